@@ -1,0 +1,166 @@
+/*
+ * tfhe_b200.h -- C ABI of the B200-native gate-bootstrapping path for zig-tfhe.
+ *
+ * The reference (thedonutfactory/zig-tfhe, pure Zig) has no FFI layer; its seams for this path
+ * are Zig-level.  Each entry point below names the reference interface it
+ * replaces (file:line under /root/reference/) -- these are exactly the functions a Zig
+ * `extern fn` block binds (see INTEGRATION.md and zig-tfhe_b200/zig/cuda.zig).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all multi-byte data little-endian, row-major.
+ *   - host entry points take HOST pointers (pageable or pinned) owned by the caller and are
+ *     synchronous: when they return, `out` is filled.
+ *   - `_device` entry points take DEVICE pointers valid on the context's device `dev`, enqueue
+ *     on that device's stream (tfhe_b200_stream) and return without synchronising.
+ *   - return value: 0 = TFHE_B200_OK, otherwise a tfhe_b200_status; tfhe_b200_last_error()
+ *     gives the message.  There is NO CPU fallback: without a usable CUDA device every call fails.
+ *   - a context is not thread-safe (one per calling thread, or lock externally), like the
+ *     reference's per-thread FFT plan (src/fft.zig:983-992).
+ *
+ * Ciphertext layouts (identical to the reference's in-memory arrays)
+ *   TLWELv0  : uint32_t[n+1], mask a[0..n), body b at index n          (src/tlwe.zig:11-31)
+ *   TLWELv1  : uint32_t[N+1]                                           (src/tlwe.zig:243-262)
+ *   TRLWELv1 : uint32_t[2][N]  = a[N] then b[N]                        (src/trlwe.zig:15-17)
+ *   CloudKey.bootstrapping_key : double[n][2L][2 (a,b)][N], each polynomial the reference's
+ *       ifft1024 spectrum, re[0..512) then im[0..512), reference bin order
+ *                                                                      (src/key.zig:61-65, src/trgsw.zig:75-91, src/trlwe.zig:104-132)
+ *   CloudKey.key_switching_key : uint32_t[N*t*base][n+1], row = base*t*i + base*j + k; rows with
+ *       k == 0 are never read                                          (src/key.zig:148-172, src/trgsw.zig:491)
+ */
+#ifndef TFHE_B200_H
+#define TFHE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tfhe_b200_ctx tfhe_b200_ctx;
+
+/* runtime mirror of params.SecurityParams / TrgswParams (src/params.zig:36-67);
+ * N must be 1024 (true for all 11 sets, src/params.zig:85-365). */
+typedef struct {
+    int32_t n;       /* tlwe_lv0.n   */
+    int32_t N;       /* trgsw_lv1.n  */
+    int32_t L;       /* trgsw_lv1.l  (1..3) */
+    int32_t bgbit;   /* trgsw_lv1.bgbit */
+    int32_t basebit; /* trgsw_lv1.basebit */
+    int32_t iks_t;   /* trgsw_lv1.iks_t */
+} tfhe_b200_params;
+
+typedef enum {
+    TFHE_B200_OK = 0,
+    TFHE_B200_ERR_INVALID = 1,     /* bad argument / unsupported parameter set */
+    TFHE_B200_ERR_NO_DEVICE = 2,   /* no CUDA device, or device is not sm_100 */
+    TFHE_B200_ERR_CUDA = 3,        /* CUDA runtime error (see last_error) */
+    TFHE_B200_ERR_NO_KEY = 4,      /* hot-path call before load_key */
+    TFHE_B200_ERR_NOT_IMPLEMENTED = 5
+} tfhe_b200_status;
+
+/* gate opcodes: the ten bootstrapped two-input gates of Gates (src/gates.zig:48-121) */
+typedef enum {
+    TFHE_B200_NAND = 0,  /* gates.zig:48  */
+    TFHE_B200_OR = 1,    /* gates.zig:57  */
+    TFHE_B200_AND = 2,   /* gates.zig:64  */
+    TFHE_B200_XOR = 3,   /* gates.zig:71  (a + 2b + 1/4) */
+    TFHE_B200_XNOR = 4,  /* gates.zig:78  (a - 2b - 1/4, reference semantics kept) */
+    TFHE_B200_NOR = 5,   /* gates.zig:85  */
+    TFHE_B200_ANDNY = 6, /* gates.zig:94  */
+    TFHE_B200_ANDYN = 7, /* gates.zig:102 */
+    TFHE_B200_ORNY = 8,  /* gates.zig:109 */
+    TFHE_B200_ORYN = 9   /* gates.zig:117 */
+} tfhe_b200_gate;
+
+/* arithmetic mode of the blind rotation */
+typedef enum {
+    TFHE_B200_MODE_FAST = 0,  /* radix-8 FMA transform; bit-identical to the reference on L=3/BGBIT=6 sets */
+    TFHE_B200_MODE_EXACT = 1  /* replays the reference's radix-2 / recurrence-twiddle / no-FMA DAG (fft.zig:582-619) */
+} tfhe_b200_mode;
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+/* Replaces nothing in the reference (it has no device); one context owns n_dev devices and
+ * replicates the keys on each (the CPU thread pool of src/parallel/thread_pool.zig:39-83 is
+ * what this sharding stands in for).  device_ids == NULL -> devices 0..n_dev-1. */
+int tfhe_b200_create(const tfhe_b200_params *params, const int *device_ids, int n_dev, tfhe_b200_ctx **out);
+void tfhe_b200_destroy(tfhe_b200_ctx *ctx);
+const char *tfhe_b200_last_error(const tfhe_b200_ctx *ctx);
+int tfhe_b200_num_devices(const tfhe_b200_ctx *ctx);
+const char *tfhe_b200_version(void);
+
+/* ---- keys: CloudKey (src/key.zig:61-77) --------------------------------------------- */
+/* Uploads + re-lays-out the cloud key on every device of the context.
+ * ksk may be NULL (CloudKey.newNoKsk, src/key.zig:80-100): key-switching calls then fail.
+ * ksk_row_stride_bytes: distance between consecutive KSK rows (>= (n+1)*4). */
+int tfhe_b200_load_key(tfhe_b200_ctx *ctx, const double *bsk, const uint32_t *ksk,
+                       size_t ksk_row_stride_bytes, uint32_t decomposition_offset);
+/* Same, from DEVICE buffers already resident on device `dev` (e.g. after an NCCL broadcast);
+ * layouts as above, KSK rows packed ((n+1)*4 bytes). */
+int tfhe_b200_load_key_device(tfhe_b200_ctx *ctx, int dev, const double *d_bsk, const uint32_t *d_ksk,
+                              uint32_t decomposition_offset);
+int tfhe_b200_set_mode(tfhe_b200_ctx *ctx, int mode);
+
+/* ---- hot path, host buffers ---------------------------------------------------------- */
+/* gates.batchNand/And/Or/Xor/Nor/Xnor (src/gates.zig:244-295, placeholders returning
+ * error.NotImplemented) and the scalar Gates.*Gate (src/gates.zig:48-121): out[i] = gate(a[i], b[i]).
+ * a, b, out: [B][n+1].  The batch is split contiguously over the context's devices. */
+int tfhe_b200_gate_batch(tfhe_b200_ctx *ctx, int op, const uint32_t *a, const uint32_t *b, uint32_t *out, size_t B);
+/* same with one opcode per item (mixed AND/XOR batches, one circuit level) */
+int tfhe_b200_gate_batch_ops(tfhe_b200_ctx *ctx, const int32_t *ops, const uint32_t *a, const uint32_t *b,
+                             uint32_t *out, size_t B);
+/* VanillaBootstrap.bootstrap (src/bootstrap/vanilla.zig:38-52) over a batch; in/out [B][n+1].
+ * testvec == NULL -> CloudKey.blind_rotate_testvec (src/key.zig:134-145); else a TRLWE [2][N]
+ * shared by the batch (tv_per_item == 0) or one per item [B][2][N] (tv_per_item != 0):
+ * trgsw.blindRotateWithTestvec (src/trgsw.zig:336-400) + sampleExtractIndex(.,0) + identityKeySwitching,
+ * i.e. the programmable (LUT) bootstrap the reference documents in src/lut.zig:42. */
+int tfhe_b200_bootstrap_batch(tfhe_b200_ctx *ctx, const uint32_t *in, uint32_t *out, size_t B,
+                              const uint32_t *testvec, int tv_per_item);
+/* VanillaBootstrap.bootstrapWithoutKeySwitch (src/bootstrap/vanilla.zig:58-69): blind rotation +
+ * sampleExtractIndex2(.,0) (src/trlwe.zig:165-180); out [B][n+1]. */
+int tfhe_b200_bootstrap_no_keyswitch_batch(tfhe_b200_ctx *ctx, const uint32_t *in, uint32_t *out, size_t B);
+/* trgsw.batchBlindRotate / blindRotate / blindRotateWithTestvec (src/trgsw.zig:290-436):
+ * parity tap, trlwe_out [B][2][N]. */
+int tfhe_b200_blind_rotate_batch(tfhe_b200_ctx *ctx, const uint32_t *in, uint32_t *trlwe_out, size_t B,
+                                 const uint32_t *testvec, int tv_per_item);
+/* trgsw.identityKeySwitching (src/trgsw.zig:471-502) over a batch: lv1 [B][N+1] -> lv0 [B][n+1]. */
+int tfhe_b200_keyswitch_batch(tfhe_b200_ctx *ctx, const uint32_t *lv1, uint32_t *lv0, size_t B);
+/* trlwe.sampleExtractIndex(., 0) (src/trlwe.zig:146-162) fused after the blind rotation:
+ * in [B][n+1] -> lv1 [B][N+1] (parity tap between blind rotation and key switch). */
+int tfhe_b200_blind_rotate_extract_batch(tfhe_b200_ctx *ctx, const uint32_t *in, uint32_t *lv1_out, size_t B);
+/* Gates.notGate / copy (src/gates.zig:131-141): no bootstrap, out = -a. */
+int tfhe_b200_not_batch(tfhe_b200_ctx *ctx, const uint32_t *a, uint32_t *out, size_t B);
+
+/* ---- hot path, device buffers (single device `dev` of the context, asynchronous) ------- */
+int tfhe_b200_gate_batch_device(tfhe_b200_ctx *ctx, int dev, int op, const int32_t *d_ops, const uint32_t *d_a,
+                                const uint32_t *d_b, uint32_t *d_out, size_t B);
+int tfhe_b200_bootstrap_batch_device(tfhe_b200_ctx *ctx, int dev, const uint32_t *d_in, uint32_t *d_out, size_t B,
+                                     const uint32_t *d_testvec, int tv_per_item);
+int tfhe_b200_blind_rotate_batch_device(tfhe_b200_ctx *ctx, int dev, const uint32_t *d_in, uint32_t *d_trlwe_out,
+                                        size_t B, const uint32_t *d_testvec, int tv_per_item);
+int tfhe_b200_keyswitch_batch_device(tfhe_b200_ctx *ctx, int dev, const uint32_t *d_lv1, uint32_t *d_lv0, size_t B);
+/* cudaStream_t of device `dev` (as void*), and a full synchronisation of all devices */
+void *tfhe_b200_stream(tfhe_b200_ctx *ctx, int dev);
+int tfhe_b200_sync(tfhe_b200_ctx *ctx);
+
+/* ---- instrumentation ----------------------------------------------------------------- */
+/* Largest |t - round(t)| seen in the inverse-transform rounding epilogue (src/fft.zig:416-424)
+ * since the last reset, over all devices; tracked only while enabled (slower kernel variant).
+ * Standing proof of the exactness margin claimed for the L=3/BGBIT=6 sets (alarm above 0.25). */
+int tfhe_b200_track_margin(tfhe_b200_ctx *ctx, int enable);
+double tfhe_b200_max_round_margin(tfhe_b200_ctx *ctx, int reset);
+/* number of kernels this library launched since the context was created (bench `gpu_launches`) */
+uint64_t tfhe_b200_launch_count(const tfhe_b200_ctx *ctx);
+/* tuning knobs (tests/bench): "kct" ciphertexts per CTA of the blind-rotation kernel (0 = default),
+ * "use_tma" 0/1, "max_chunk" ciphertexts per launch, "timing" 0/1 (record CUDA events around K1/K2) */
+int tfhe_b200_set_tuning(tfhe_b200_ctx *ctx, const char *key, int value);
+/* with "timing" on: device time in ms of the last blind-rotation (which = 0) or key-switch (which = 1)
+ * kernel enqueued on device `dev`, measured with CUDA events on the launching stream */
+double tfhe_b200_last_kernel_ms(tfhe_b200_ctx *ctx, int dev, int which);
+/* microbenchmarks used for the roofline denominators (profiles/): returns achieved rate */
+double tfhe_b200_measure_fp64_tflops(tfhe_b200_ctx *ctx, int dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,360 @@
+// blind_rotate.cu -- K1: fused gate-linear-part + blind rotation + sample extraction for sm_100a.
+//
+// Replaces, for a batch of ciphertexts at once:
+//   Gates.*Gate linear parts            src/gates.zig:48-121   (fused prologue)
+//   trgsw.blindRotate / WithTestvec     src/trgsw.zig:290-400
+//     polyMulWithXK                     src/trgsw.zig:442-466  (index arithmetic, never materialised)
+//     cmux                              src/trgsw.zig:260-284
+//     externalProductWithFft            src/trgsw.zig:111-154
+//       decompositionIntoStorage        src/trgsw.zig:193-219  (digits produced in registers)
+//       ifft1024 x 2L, fmaInFd1024, fft1024 x 2   src/fft.zig:293-443, src/trgsw.zig:157-189
+//   trlwe.sampleExtractIndex(., 0)      src/trlwe.zig:146-162  (fused epilogue)
+//
+// Execution model.  One CTA = KCT groups of 64 threads (KCT = 6: 12 warps, 3 per SM sub-partition, 168 registers).  A group owns one
+// ciphertext for all n iterations: its TRLWE accumulator (2 x 1024 u32) never leaves shared memory,
+// the 2L digit spectra never leave registers (each is consumed by the pointwise MAC as soon as its
+// last radix-8 pass finishes), and the two output spectra are 16 complex accumulators per thread.
+// The bootstrapping key is streamed chunk by chunk (one chunk = the a and b spectra of one gadget
+// row, 16 KiB) by cp.async.bulk into an NST-deep shared-memory ring guarded by mbarriers, so the
+// KCT ciphertexts of the CTA share each chunk and every CTA of the wave hits the same L2 lines.
+// There is no dedicated producer warp (a 13th warp would cap the kernel at 128 registers): thread 0
+// polls the ring's empty barriers at the exchange points of its own transforms and issues the next
+// bulk copy as soon as a stage has been released by all groups.
+//
+// No tensor cores: the pointwise MAC is not a contraction and the 512-point transforms are FP64.
+#include <cuda_runtime.h>
+
+#include "kernels.cuh"
+#include "negacyclic_fft.cuh"
+
+namespace tfhe_b200 {
+
+namespace {
+
+constexpr int kStages = 3;  // depth of the key ring (16 KiB per stage)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (TMA engine)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Key-ring producer state, live only in thread 0 of the CTA (see header comment).
+struct Producer {
+    const cplx *src;      // next chunk in global memory
+    cplx *ring;
+    uint64_t *full_bar, *empty_bar;
+    int remaining;        // chunks still to issue
+    int issued;           // chunks issued so far (first kStages need no empty wait)
+    int stage;
+    uint32_t phase;
+    bool active;
+};
+__device__ __forceinline__ void producer_poll(Producer &pr) {
+    if (pr.active && pr.remaining > 0) {
+        if (pr.issued < kStages || mbar_try_wait(&pr.empty_bar[pr.stage], pr.phase ^ 1)) {
+            mbar_arrive_expect_tx(&pr.full_bar[pr.stage], kBskChunkBytes);
+            bulk_g2s(pr.ring + pr.stage * kBskChunkCplx, pr.src, kBskChunkBytes, &pr.full_bar[pr.stage]);
+            pr.src += kBskChunkCplx;
+            pr.remaining--;
+            pr.issued++;
+            if (++pr.stage == kStages) { pr.stage = 0; pr.phase ^= 1; }
+        }
+    }
+}
+
+// linear part of the ten bootstrapped gates (gates.zig:48-121); op < 0: identity (plain bootstrap)
+__device__ __forceinline__ uint32_t gate_linear(int op, uint32_t a, uint32_t b) {
+    switch (op) {
+        case 0: case 5: return 0u - a - b;   // NAND, NOR      : -a - b
+        case 1: case 2: return a + b;        // OR, AND        :  a + b
+        case 3: return a + 2u * b;           // XOR            :  a + 2b   (addMul, gates.zig:72)
+        case 4: return a - 2u * b;           // XNOR           :  a - 2b   (subMul, gates.zig:79)
+        case 6: case 8: return b - a;        // ANDNY, ORNY    : -a + b
+        case 7: case 9: return a - b;        // ANDYN, ORYN    :  a - b
+        default: return a;
+    }
+}
+// constant added to the body: f64ToTorus(+-1/8, +-1/4) (utils.zig:28-33)
+__device__ __forceinline__ uint32_t gate_constant(int op) {
+    switch (op) {
+        case 0: case 1: case 8: case 9: return 0x20000000u;   // +1/8
+        case 2: case 5: case 6: case 7: return 0xE0000000u;   // -1/8
+        case 3: return 0x40000000u;                            // +1/4
+        case 4: return 0xC0000000u;                            // -1/4
+        default: return 0u;
+    }
+}
+
+// forward transform, role A registers in -> role C (leaf order) out.  2 named barriers + 1 warp sync.
+template <bool USE_TMA>
+__device__ __forceinline__ void fwd_transform(cplx (&v)[8], cplx *x1, cplx *x2, const cplx *tw2s, const cplx *tw3s, int t,
+                                              int hi, int lo, int barid, Producer &pr) {
+    fwd_pass1(v);
+#pragma unroll
+    for (int q = 0; q < 8; q++) x1[x1_slot(hi, q, lo)] = v[q];
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; q++) v[q] = x1[x1_slot(hi, lo, q)];
+    fwd_pass(v, tw2s + lo, 8);
+    if (USE_TMA) producer_poll(pr);
+    bar_sync(barid, kGroupThreads);  // every reader of the previous X2 contents is done
+#pragma unroll
+    for (int q = 0; q < 8; q++) x2[x2_slot(lo, q, hi)] = v[q];
+    bar_sync(barid, kGroupThreads);
+#pragma unroll
+    for (int q = 0; q < 8; q++) v[q] = x2[x2_slot(hi, lo, q)];
+    fwd_pass(v, tw3s + t, 64);
+}
+
+// inverse transform, role C (leaf order) in -> role A out: v[p] = c_e, e = 64 p + 8 lo + hi
+template <bool USE_TMA>
+__device__ __forceinline__ void inv_transform(cplx (&v)[8], cplx *x1, cplx *x2, const cplx *tw2s, const cplx *tw3s, int t,
+                                              int hi, int lo, int barid, Producer &pr) {
+    inv_pass(v, tw3s + t, 64);
+    if (USE_TMA) producer_poll(pr);
+    bar_sync(barid, kGroupThreads);
+#pragma unroll
+    for (int q = 0; q < 8; q++) x2[x2_slot(hi, lo, q)] = v[q];
+    bar_sync(barid, kGroupThreads);
+#pragma unroll
+    for (int q = 0; q < 8; q++) v[q] = x2[x2_slot(lo, q, hi)];
+    inv_pass(v, tw2s + lo, 8);
+#pragma unroll
+    for (int q = 0; q < 8; q++) x1[x1_slot(hi, lo, q)] = v[q];
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; q++) v[q] = x1[x1_slot(hi, q, lo)];
+    inv_pass1(v);
+}
+
+template <bool MARGIN>
+__device__ __forceinline__ void round_accumulate(const cplx (&v)[8], uint32_t *accp, int hi, int lo, int wide, double &margin) {
+#pragma unroll
+    for (int p = 0; p < 8; p++) {
+        const int e = 64 * p + 8 * lo + hi;
+        if (MARGIN) {
+            margin = fmax(margin, fabs(v[p].re - rint(v[p].re)));
+            margin = fmax(margin, fabs(v[p].im - rint(v[p].im)));
+        }
+        const uint32_t r0 = wide ? round_torus_wide(v[p].re) : round_torus_magic(v[p].re);
+        const uint32_t r1 = wide ? round_torus_wide(v[p].im) : round_torus_magic(v[p].im);
+        accp[e] += r0;
+        accp[e + kHalfN] += r1;
+    }
+}
+
+__host__ __device__ constexpr int align16(int x) { return (x + 15) & ~15; }
+
+template <int KCT, bool USE_TMA, bool MARGIN>
+__global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(const BrArgs P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // ---- carve shared memory
+    unsigned char *ptr = smem_raw;
+    cplx *bsk_ring = reinterpret_cast<cplx *>(ptr);
+    if (USE_TMA) ptr += kStages * kBskChunkBytes;
+    cplx *tw3s = reinterpret_cast<cplx *>(ptr);
+    ptr += kTw3Len * sizeof(cplx);
+    cplx *tw2s = reinterpret_cast<cplx *>(ptr);
+    ptr += kTw2Len * sizeof(cplx);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(ptr);
+    uint64_t *empty_bar = full_bar + kStages;
+    ptr += 2 * kStages * sizeof(uint64_t) + 16;
+    const int n = P.n, L = P.L, bgbit = P.bgbit;
+    const int group_bytes = 3 * 8192 + align16((n + 1) * 2);
+
+    const int tid = threadIdx.x;
+    const int first_ct = blockIdx.x * KCT;
+    const int n_active = min(KCT, (int)P.B - first_ct);
+
+    for (int i = tid; i < kTw3Len; i += blockDim.x) tw3s[i] = P.tw3[i];
+    for (int i = tid; i < kTw2Len; i += blockDim.x) tw2s[i] = P.tw2[i];
+    if (USE_TMA && tid == 0) {
+        for (int s = 0; s < kStages; s++) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], n_active * 2);   // one arrival per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int g = tid >> 6, t = tid & 63;
+    if (g >= n_active) return;
+    const int hi = t >> 3, lo = t & 7;
+    const int barid = 1 + g;
+    unsigned char *gb = ptr + (size_t)g * group_bytes;
+    uint32_t *acc_a = reinterpret_cast<uint32_t *>(gb);
+    uint32_t *acc_b = acc_a + kN;
+    cplx *x1 = reinterpret_cast<cplx *>(gb + 8192);
+    cplx *x2 = reinterpret_cast<cplx *>(gb + 16384);
+    uint16_t *atil = reinterpret_cast<uint16_t *>(gb + 24576);
+    const size_t ct = (size_t)first_ct + g;
+
+    // ---- prologue: gate linear part (gates.zig:48-121) + modulus switch (trgsw.zig:297,312)
+    {
+        const int op = P.ops ? P.ops[ct] : P.op;
+        const uint32_t *ia = P.in_a + ct * (size_t)(n + 1);
+        const uint32_t *ib = (op >= 0) ? P.in_b + ct * (size_t)(n + 1) : ia;
+        for (int i = t; i <= n; i += kGroupThreads) {
+            uint32_t lin = gate_linear(op, ia[i], ib[i]);
+            if (i == n) lin += gate_constant(op);
+            const uint32_t m = (uint32_t)(((unsigned long long)lin + (1u << 20)) >> 21);   // in [0, 2N]
+            atil[i] = (uint16_t)((i == n) ? (2 * kN - m) : m);
+        }
+    }
+    bar_sync(barid, kGroupThreads);
+    // ---- acc = X^btil * testvec (trgsw.zig:300-306)
+    {
+        const int btil = atil[n];
+        const uint32_t *tv = P.testvec ? P.testvec + (P.tv_per_item ? ct * (size_t)(2 * kN) : 0) : nullptr;
+        for (int j = t; j < kN; j += kGroupThreads) {
+            const int u = (j - btil) & (2 * kN - 1);
+            const uint32_t va = tv ? tv[u & (kN - 1)] : 0u;
+            const uint32_t vb = tv ? tv[kN + (u & (kN - 1))] : 0x20000000u;   // key.zig:134-145
+            acc_a[j] = (u & kN) ? 0u - va : va;
+            acc_b[j] = (u & kN) ? 0u - vb : vb;
+        }
+    }
+    bar_sync(barid, kGroupThreads);
+
+    const uint32_t mask = (1u << bgbit) - 1u, half_bg = 1u << (bgbit - 1);
+    const uint32_t offset = P.offset;
+    const int wide = P.wide_round;
+    int stage = 0;
+    uint32_t phase = 0;
+    double margin = 0.0;
+    Producer pr;
+    pr.src = P.bsk; pr.ring = bsk_ring; pr.full_bar = full_bar; pr.empty_bar = empty_bar;
+    pr.remaining = USE_TMA ? n * 2 * L : 0; pr.issued = 0; pr.stage = 0; pr.phase = 0;
+    pr.active = USE_TMA && tid == 0;
+    if (USE_TMA) { producer_poll(pr); producer_poll(pr); producer_poll(pr); }   // fill the ring
+
+    // ---- n CMUX steps (trgsw.zig:311-330)
+    for (int i = 0; i < n; i++) {
+        const int at = atil[i];
+        cplx oa[8], ob[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) { oa[q] = cplx{0.0, 0.0}; ob[q] = cplx{0.0, 0.0}; }
+
+#pragma unroll 1
+        for (int h = 0; h < 2; h++) {          // h = 0: digits of the a polynomial, 1: of b (trgsw.zig:211-217)
+            const uint32_t *accp = h ? acc_b : acc_a;
+            uint32_t d[16];
+            load_rot_diffs(d, accp, at, offset, hi, lo);
+#pragma unroll 1
+            for (int l = 0; l < L; l++) {
+                cplx v[8];
+                digits_to_cplx(v, d, 32 - (l + 1) * bgbit, mask, half_bg);
+                fwd_transform<USE_TMA>(v, x1, x2, tw2s, tw3s, t, hi, lo, barid, pr);
+                const cplx *chunk;
+                if (USE_TMA) {
+                    while (!mbar_try_wait(&full_bar[stage], phase)) producer_poll(pr);
+                    chunk = bsk_ring + stage * kBskChunkCplx;
+                } else {
+                    chunk = P.bsk + ((size_t)i * 2 * L + h * L + l) * kBskChunkCplx;
+                }
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    cmac(oa[q], v[q], chunk[bsk_slot(0, q, t)]);
+                    cmac(ob[q], v[q], chunk[bsk_slot(1, q, t)]);
+                }
+                if (USE_TMA) {
+                    __syncwarp();
+                    if ((t & 31) == 0) mbar_arrive(&empty_bar[stage]);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        inv_transform<USE_TMA>(oa, x1, x2, tw2s, tw3s, t, hi, lo, barid, pr);
+        round_accumulate<MARGIN>(oa, acc_a, hi, lo, wide, margin);
+        inv_transform<USE_TMA>(ob, x1, x2, tw2s, tw3s, t, hi, lo, barid, pr);
+        round_accumulate<MARGIN>(ob, acc_b, hi, lo, wide, margin);
+        bar_sync(barid, kGroupThreads);   // accumulator complete before the next rotated reads
+    }
+
+    // ---- epilogue
+    if (P.out_trlwe) {
+        uint32_t *o = P.out_trlwe + ct * (size_t)(2 * kN);
+        for (int j = t; j < kN; j += kGroupThreads) { o[j] = acc_a[j]; o[kN + j] = acc_b[j]; }
+    }
+    if (P.out_lv1) {   // sampleExtractIndex(., 0): trlwe.zig:146-162
+        uint32_t *o = P.out_lv1 + ct * (size_t)(kN + 1);
+        for (int j = t; j <= kN; j += kGroupThreads)
+            o[j] = (j == 0) ? acc_a[0] : (j == kN) ? acc_b[0] : 0u - acc_a[kN - j];
+    }
+    if (MARGIN && P.margin_bits) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) margin = fmax(margin, __shfl_xor_sync(0xffffffffu, margin, s));
+        if ((t & 31) == 0) atomicMax(P.margin_bits, (unsigned long long)__double_as_longlong(margin));
+    }
+}
+
+template <int KCT, bool USE_TMA, bool MARGIN>
+cudaError_t launch_variant(const BrArgs &a, cudaStream_t s) {
+    const int threads = KCT * kGroupThreads;
+    const size_t smem = (USE_TMA ? kStages * kBskChunkBytes : 0) + (kTw3Len + kTw2Len) * sizeof(cplx) + 2 * kStages * 8 + 16 +
+                        (size_t)KCT * (3 * 8192 + align16((a.n + 1) * 2));
+    auto kern = blind_rotate_kernel<KCT, USE_TMA, MARGIN>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const unsigned grid = (a.B + KCT - 1) / KCT;
+    kern<<<grid, threads, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+template <int KCT>
+cudaError_t launch_kct(const BrArgs &a, bool tma, bool margin, cudaStream_t s) {
+    if (tma) return margin ? launch_variant<KCT, true, true>(a, s) : launch_variant<KCT, true, false>(a, s);
+    return margin ? launch_variant<KCT, false, true>(a, s) : launch_variant<KCT, false, false>(a, s);
+}
+
+}  // namespace
+
+cudaError_t launch_blind_rotate(const BrArgs &a, const BrTuning &tune, bool track_margin, cudaStream_t s, uint64_t *launches) {
+    if (a.B == 0) return cudaSuccess;
+    int kct = tune.kct;
+    if (kct <= 0) kct = (a.B >= 148u * 6u) ? 6 : (a.B >= 148u * 4u) ? 4 : (a.B >= 148u * 2u) ? 2 : 1;
+    if (launches) (*launches)++;
+    switch (kct) {
+        case 1: return launch_kct<1>(a, tune.use_tma != 0, track_margin, s);
+        case 2: return launch_kct<2>(a, tune.use_tma != 0, track_margin, s);
+        case 3: return launch_kct<3>(a, tune.use_tma != 0, track_margin, s);
+        case 4: return launch_kct<4>(a, tune.use_tma != 0, track_margin, s);
+        case 5: return launch_kct<5>(a, tune.use_tma != 0, track_margin, s);
+        default: return launch_kct<6>(a, tune.use_tma != 0, track_margin, s);
+    }
+}
+
+}  // namespace tfhe_b200

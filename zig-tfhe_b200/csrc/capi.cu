@@ -1,0 +1,499 @@
+// capi.cu -- the C-ABI boundary of libtfhe_b200 (include/tfhe_b200.h): contexts, key upload and
+// re-layout, host<->device staging, batch sharding over the context's devices, kernel dispatch.
+// There is no CPU fallback anywhere in this file: every hot-path entry point launches the CUDA
+// kernels or fails with an error code.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/tfhe_b200.h"
+#include "host_tables.h"
+#include "kernels.cuh"
+
+using namespace tfhe_b200;
+
+namespace {
+
+struct Buf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct Device {
+    int id = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cplx *bsk = nullptr;
+    uint32_t *ksk = nullptr;
+    cplx *tw2 = nullptr, *tw3 = nullptr;
+    double *exact_tables = nullptr;
+    unsigned long long *margin_bits = nullptr;
+    Buf a, b, out, lv1, ops, tv, trlwe;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // K1 start, K1 end / K2 start, K2 end (timing mode)
+    bool ev_valid = false;
+};
+
+}  // namespace
+
+struct tfhe_b200_ctx {
+    tfhe_b200_params prm{};
+    std::vector<Device> devs;
+    std::string err;
+    int mode = TFHE_B200_MODE_FAST;
+    bool track_margin = false;
+    bool has_key = false, has_ksk = false;
+    uint32_t offset = 0;
+    int ksk_pitch = 0;
+    BrTuning tune;
+    uint64_t launches = 0;
+    bool timing = false;
+    size_t max_chunk = (size_t)1 << 18;   // ciphertexts per device per launch
+};
+
+namespace {
+
+int fail(tfhe_b200_ctx *c, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+#define CU(c, expr)                                                                                       \
+    do {                                                                                                  \
+        cudaError_t e__ = (expr);                                                                         \
+        if (e__ != cudaSuccess)                                                                           \
+            return fail(c, TFHE_B200_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+int ensure(tfhe_b200_ctx *c, Buf &b, size_t bytes) {
+    if (b.cap >= bytes) return 0;
+    if (b.p) CU(c, cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    CU(c, cudaMalloc(&b.p, bytes));
+    b.cap = bytes;
+    return 0;
+}
+
+bool wide_round(const tfhe_b200_params &p) {
+    // |coefficient| of the inverse transform < N * 2L * 2^(bgbit-1) * 2^31; magic rounding needs < 2^51
+    double bits = 10 + 1 + (p.L > 1 ? 2 : 0) + (p.bgbit - 1) + 31;
+    return bits >= 50;
+}
+
+// K1 (+K2) on device buffers of one device
+int run_device(tfhe_b200_ctx *c, Device &d, int op, const int32_t *d_ops, const uint32_t *d_a, const uint32_t *d_b, uint32_t *d_lv0,
+               uint32_t *d_lv1_out, uint32_t *d_trlwe, size_t B, const uint32_t *d_tv, int tv_per_item) {
+    if (!c->has_key) return fail(c, TFHE_B200_ERR_NO_KEY, "no cloud key loaded");
+    if (B == 0) return 0;
+    CU(c, cudaSetDevice(d.id));
+    uint32_t *lv1 = d_lv1_out;
+    if (d_lv0 && !lv1) {
+        if (int r = ensure(c, d.lv1, B * (size_t)(kN + 1) * 4)) return r;
+        lv1 = (uint32_t *)d.lv1.p;
+    }
+    BrArgs A{};
+    A.in_a = d_a; A.in_b = d_b; A.ops = d_ops; A.op = op;
+    A.bsk = d.bsk; A.tw2 = d.tw2; A.tw3 = d.tw3;
+    A.testvec = d_tv; A.tv_per_item = tv_per_item;
+    A.out_lv1 = lv1; A.out_trlwe = d_trlwe;
+    A.margin_bits = c->track_margin ? d.margin_bits : nullptr;
+    A.B = (uint32_t)B; A.n = c->prm.n; A.L = c->prm.L; A.bgbit = c->prm.bgbit;
+    A.offset = c->offset; A.wide_round = wide_round(c->prm) ? 1 : 0;
+    d.ev_valid = false;
+    if (c->timing) CU(c, cudaEventRecord(d.ev[0], d.stream));
+    if (c->mode == TFHE_B200_MODE_EXACT) {
+        if (!d.exact_tables) return fail(c, TFHE_B200_ERR_NOT_IMPLEMENTED, "exact mode tables missing");
+        CU(c, launch_blind_rotate_exact(A, d.exact_tables, d.stream, &c->launches));
+    } else {
+        CU(c, launch_blind_rotate(A, c->tune, c->track_margin, d.stream, &c->launches));
+    }
+    if (c->timing) CU(c, cudaEventRecord(d.ev[1], d.stream));
+    if (d_lv0) {
+        if (!c->has_ksk) return fail(c, TFHE_B200_ERR_NO_KEY, "no key-switching key loaded");
+        KsArgs K{lv1, d_lv0, d.ksk, (uint32_t)B, c->prm.n, c->prm.basebit, c->prm.iks_t, c->ksk_pitch};
+        CU(c, launch_keyswitch(K, d.sm_count, d.stream, &c->launches));
+    }
+    if (c->timing) {
+        CU(c, cudaEventRecord(d.ev[2], d.stream));
+        d.ev_valid = true;
+    }
+    return 0;
+}
+
+enum class Out { LV0, LV0_NOKS, LV1, TRLWE };
+
+// host-buffer driver: shard contiguously over devices, chunk, stage, launch, copy back
+int run_host(tfhe_b200_ctx *c, int op, const int32_t *ops, const uint32_t *a, const uint32_t *b, void *out, Out kind, size_t B,
+             const uint32_t *tv, int tv_per_item) {
+    if (!c) return TFHE_B200_ERR_INVALID;
+    if (!c->has_key) return fail(c, TFHE_B200_ERR_NO_KEY, "no cloud key loaded");
+    if (B == 0) return 0;
+    if (!a || !out || ((op >= 0 || ops) && !b)) return fail(c, TFHE_B200_ERR_INVALID, "null buffer");
+    const size_t w0 = (size_t)c->prm.n + 1, w1 = (size_t)kN + 1, wt = (size_t)2 * kN;
+    const size_t wout = (kind == Out::LV0 || kind == Out::LV0_NOKS) ? w0 : (kind == Out::LV1) ? w1 : wt;
+    const int nd = (int)c->devs.size();
+    const bool two_inputs = (op >= 0 || ops);
+    // all devices proceed chunk-round by chunk-round; within a round work is asynchronous per device
+    std::vector<size_t> lo(nd), hi(nd), pos(nd);
+    for (int k = 0; k < nd; k++) { lo[k] = B * k / nd; hi[k] = B * (k + 1) / nd; pos[k] = lo[k]; }
+    bool more = true;
+    while (more) {
+        more = false;
+        for (int k = 0; k < nd; k++) {
+            Device &d = c->devs[k];
+            const size_t nb = std::min(c->max_chunk, hi[k] - pos[k]);
+            if (nb == 0) continue;
+            const size_t off = pos[k];
+            CU(c, cudaSetDevice(d.id));
+            if (int r = ensure(c, d.a, nb * w0 * 4)) return r;
+            CU(c, cudaMemcpyAsync(d.a.p, a + off * w0, nb * w0 * 4, cudaMemcpyHostToDevice, d.stream));
+            if (two_inputs) {
+                if (int r = ensure(c, d.b, nb * w0 * 4)) return r;
+                CU(c, cudaMemcpyAsync(d.b.p, b + off * w0, nb * w0 * 4, cudaMemcpyHostToDevice, d.stream));
+            }
+            const int32_t *d_ops = nullptr;
+            if (ops) {
+                if (int r = ensure(c, d.ops, nb * 4)) return r;
+                CU(c, cudaMemcpyAsync(d.ops.p, ops + off, nb * 4, cudaMemcpyHostToDevice, d.stream));
+                d_ops = (const int32_t *)d.ops.p;
+            }
+            const uint32_t *d_tv = nullptr;
+            if (tv) {
+                const size_t tvb = (tv_per_item ? nb : 1) * wt * 4;
+                if (int r = ensure(c, d.tv, tvb)) return r;
+                CU(c, cudaMemcpyAsync(d.tv.p, tv + (tv_per_item ? off * wt : 0), tvb, cudaMemcpyHostToDevice, d.stream));
+                d_tv = (const uint32_t *)d.tv.p;
+            }
+            if (int r = ensure(c, d.out, nb * wout * 4)) return r;
+            uint32_t *d_out = (uint32_t *)d.out.p;
+            int r = 0;
+            if (kind == Out::LV0)
+                r = run_device(c, d, ops ? 0 : op, d_ops, (uint32_t *)d.a.p, (uint32_t *)d.b.p, d_out, nullptr, nullptr, nb, d_tv, tv_per_item);
+            else if (kind == Out::LV1)
+                r = run_device(c, d, ops ? 0 : op, d_ops, (uint32_t *)d.a.p, (uint32_t *)d.b.p, nullptr, d_out, nullptr, nb, d_tv, tv_per_item);
+            else if (kind == Out::TRLWE)
+                r = run_device(c, d, ops ? 0 : op, d_ops, (uint32_t *)d.a.p, (uint32_t *)d.b.p, nullptr, nullptr, d_out, nb, d_tv, tv_per_item);
+            else {  // LV0_NOKS: blind rotate + extract, then keep the first n mask entries + body
+                if (int r2 = ensure(c, d.lv1, nb * w1 * 4)) return r2;
+                r = run_device(c, d, ops ? 0 : op, d_ops, (uint32_t *)d.a.p, (uint32_t *)d.b.p, nullptr, (uint32_t *)d.lv1.p, nullptr, nb, d_tv,
+                               tv_per_item);
+                if (!r) CU(c, launch_extract2((uint32_t *)d.lv1.p, d_out, (uint32_t)nb, c->prm.n, d.stream, &c->launches));
+            }
+            if (r) return r;
+            CU(c, cudaMemcpyAsync((uint32_t *)out + off * wout, d_out, nb * wout * 4, cudaMemcpyDeviceToHost, d.stream));
+            pos[k] += nb;
+            if (pos[k] < hi[k]) more = true;
+        }
+        for (int k = 0; k < nd; k++) {
+            CU(c, cudaSetDevice(c->devs[k].id));
+            CU(c, cudaStreamSynchronize(c->devs[k].stream));
+        }
+    }
+    return 0;
+}
+
+int upload_key_device(tfhe_b200_ctx *c, Device &d, const double *src_bsk, bool bsk_on_device, const uint32_t *src_ksk,
+                      bool ksk_on_device, size_t ksk_stride_u32) {
+    const tfhe_b200_params &p = c->prm;
+    CU(c, cudaSetDevice(d.id));
+    const size_t bsk_doubles = (size_t)p.n * 2 * p.L * 2 * kN;
+    const double *d_ref = src_bsk;
+    double *staging = nullptr;
+    if (!bsk_on_device) {
+        CU(c, cudaMalloc(&staging, bsk_doubles * 8));
+        CU(c, cudaMemcpyAsync(staging, src_bsk, bsk_doubles * 8, cudaMemcpyHostToDevice, d.stream));
+        d_ref = staging;
+    }
+    if (d.bsk) CU(c, cudaFree(d.bsk));
+    CU(c, cudaMalloc(&d.bsk, bsk_doubles * 8));
+    CU(c, launch_permute_bsk(d_ref, d.bsk, p.n, p.L, d.stream, &c->launches));
+    CU(c, cudaStreamSynchronize(d.stream));
+    if (staging) CU(c, cudaFree(staging));
+
+    if (d.ksk) { CU(c, cudaFree(d.ksk)); d.ksk = nullptr; }
+    if (src_ksk) {
+        const int base = 1 << p.basebit;
+        const size_t rows = (size_t)kN * p.iks_t * base;
+        const uint32_t *d_refk = src_ksk;
+        uint32_t *stg = nullptr;
+        if (!ksk_on_device) {
+            CU(c, cudaMalloc(&stg, rows * ksk_stride_u32 * 4));
+            CU(c, cudaMemcpyAsync(stg, src_ksk, rows * ksk_stride_u32 * 4, cudaMemcpyHostToDevice, d.stream));
+            d_refk = stg;
+        }
+        CU(c, cudaMalloc(&d.ksk, (size_t)kN * p.iks_t * (base - 1) * c->ksk_pitch * 4));
+        CU(c, launch_repack_ksk(d_refk, ksk_stride_u32, d.ksk, p.n, p.basebit, p.iks_t, c->ksk_pitch, d.stream, &c->launches));
+        CU(c, cudaStreamSynchronize(d.stream));
+        if (stg) CU(c, cudaFree(stg));
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *tfhe_b200_version(void) { return "tfhe_b200 0.1 (sm_100a)"; }
+
+int tfhe_b200_create(const tfhe_b200_params *params, const int *device_ids, int n_dev, tfhe_b200_ctx **out) {
+    if (!params || !out || n_dev < 1) return TFHE_B200_ERR_INVALID;
+    *out = nullptr;
+    const tfhe_b200_params &p = *params;
+    if (p.N != kN || p.n < 1 || p.n > 4096 || p.L < 1 || p.L > 4 || p.bgbit < 1 || p.L * p.bgbit > 32 || p.basebit < 1 ||
+        p.basebit > 8 || p.iks_t < 1 || 1 + p.basebit * p.iks_t > 32)
+        return TFHE_B200_ERR_INVALID;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count < 1) return TFHE_B200_ERR_NO_DEVICE;
+    auto *c = new tfhe_b200_ctx();
+    c->prm = p;
+    c->ksk_pitch = ((p.n + 1) + 3) & ~3;
+    cplx tw2[kTw2Len], tw3[kTw3Len];
+    make_twiddle_tables(tw2, tw3);
+    for (int k = 0; k < n_dev; k++) {
+        Device d;
+        d.id = device_ids ? device_ids[k] : k;
+        cudaDeviceProp prop{};
+        if (d.id < 0 || d.id >= count || cudaGetDeviceProperties(&prop, d.id) != cudaSuccess || prop.major != 10) {
+            delete c;
+            return TFHE_B200_ERR_NO_DEVICE;   // kernels are built for sm_100a only
+        }
+        d.sm_count = prop.multiProcessorCount;
+        bool ok = cudaSetDevice(d.id) == cudaSuccess && cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaMalloc(&d.tw2, sizeof(tw2)) == cudaSuccess && cudaMalloc(&d.tw3, sizeof(tw3)) == cudaSuccess &&
+                  cudaMalloc(&d.margin_bits, 8) == cudaSuccess && cudaEventCreate(&d.ev[0]) == cudaSuccess &&
+                  cudaEventCreate(&d.ev[1]) == cudaSuccess && cudaEventCreate(&d.ev[2]) == cudaSuccess &&
+                  cudaMemcpy(d.tw2, tw2, sizeof(tw2), cudaMemcpyHostToDevice) == cudaSuccess &&
+                  cudaMemcpy(d.tw3, tw3, sizeof(tw3), cudaMemcpyHostToDevice) == cudaSuccess &&
+                  cudaMemset(d.margin_bits, 0, 8) == cudaSuccess;
+        c->devs.push_back(d);
+        if (!ok) {
+            tfhe_b200_destroy(c);
+            return TFHE_B200_ERR_CUDA;
+        }
+    }
+    *out = c;
+    return TFHE_B200_OK;
+}
+
+void tfhe_b200_destroy(tfhe_b200_ctx *c) {
+    if (!c) return;
+    for (Device &d : c->devs) {
+        cudaSetDevice(d.id);
+        if (d.stream) cudaStreamSynchronize(d.stream);
+        for (void *p : {(void *)d.bsk, (void *)d.ksk, (void *)d.tw2, (void *)d.tw3, (void *)d.exact_tables, (void *)d.margin_bits, d.a.p, d.b.p,
+                        d.out.p, d.lv1.p, d.ops.p, d.tv.p, d.trlwe.p})
+            if (p) cudaFree(p);
+        for (cudaEvent_t e : d.ev) if (e) cudaEventDestroy(e);
+        if (d.stream) cudaStreamDestroy(d.stream);
+    }
+    delete c;
+}
+
+const char *tfhe_b200_last_error(const tfhe_b200_ctx *c) { return c ? c->err.c_str() : "null context"; }
+int tfhe_b200_num_devices(const tfhe_b200_ctx *c) { return c ? (int)c->devs.size() : 0; }
+
+int tfhe_b200_load_key(tfhe_b200_ctx *c, const double *bsk, const uint32_t *ksk, size_t ksk_row_stride_bytes, uint32_t offset) {
+    if (!c || !bsk) return fail(c, TFHE_B200_ERR_INVALID, "null key");
+    size_t stride = (size_t)c->prm.n + 1;
+    if (ksk) {
+        if (ksk_row_stride_bytes == 0) ksk_row_stride_bytes = stride * 4;
+        if (ksk_row_stride_bytes % 4 || ksk_row_stride_bytes < stride * 4) return fail(c, TFHE_B200_ERR_INVALID, "bad KSK row stride");
+        stride = ksk_row_stride_bytes / 4;
+    }
+    for (Device &d : c->devs)
+        if (int r = upload_key_device(c, d, bsk, false, ksk, false, stride)) return r;
+    c->offset = offset;
+    c->has_key = true;
+    c->has_ksk = ksk != nullptr;
+    return 0;
+}
+
+int tfhe_b200_load_key_device(tfhe_b200_ctx *c, int dev, const double *d_bsk, const uint32_t *d_ksk, uint32_t offset) {
+    if (!c || !d_bsk || dev < 0 || dev >= (int)c->devs.size()) return fail(c, TFHE_B200_ERR_INVALID, "bad argument");
+    if (int r = upload_key_device(c, c->devs[dev], d_bsk, true, d_ksk, true, (size_t)c->prm.n + 1)) return r;
+    c->offset = offset;
+    c->has_key = true;
+    c->has_ksk = d_ksk != nullptr;
+    return 0;
+}
+
+int tfhe_b200_set_mode(tfhe_b200_ctx *c, int mode) {
+    if (!c || (mode != TFHE_B200_MODE_FAST && mode != TFHE_B200_MODE_EXACT)) return fail(c, TFHE_B200_ERR_INVALID, "bad mode");
+    c->mode = mode;
+    return 0;
+}
+
+int tfhe_b200_gate_batch(tfhe_b200_ctx *c, int op, const uint32_t *a, const uint32_t *b, uint32_t *out, size_t B) {
+    if (!c || op < 0 || op > 9) return fail(c, TFHE_B200_ERR_INVALID, "bad gate opcode %d", op);
+    return run_host(c, op, nullptr, a, b, out, Out::LV0, B, nullptr, 0);
+}
+
+int tfhe_b200_gate_batch_ops(tfhe_b200_ctx *c, const int32_t *ops, const uint32_t *a, const uint32_t *b, uint32_t *out, size_t B) {
+    if (!c || !ops) return fail(c, TFHE_B200_ERR_INVALID, "null opcode array");
+    for (size_t i = 0; i < B; i++)
+        if (ops[i] < 0 || ops[i] > 9) return fail(c, TFHE_B200_ERR_INVALID, "bad gate opcode %d at %zu", ops[i], i);
+    return run_host(c, 0, ops, a, b, out, Out::LV0, B, nullptr, 0);
+}
+
+int tfhe_b200_bootstrap_batch(tfhe_b200_ctx *c, const uint32_t *in, uint32_t *out, size_t B, const uint32_t *tv, int tv_per_item) {
+    return run_host(c, -1, nullptr, in, nullptr, out, Out::LV0, B, tv, tv_per_item);
+}
+
+int tfhe_b200_bootstrap_no_keyswitch_batch(tfhe_b200_ctx *c, const uint32_t *in, uint32_t *out, size_t B) {
+    return run_host(c, -1, nullptr, in, nullptr, out, Out::LV0_NOKS, B, nullptr, 0);
+}
+
+int tfhe_b200_blind_rotate_batch(tfhe_b200_ctx *c, const uint32_t *in, uint32_t *trlwe_out, size_t B, const uint32_t *tv, int tv_per_item) {
+    return run_host(c, -1, nullptr, in, nullptr, trlwe_out, Out::TRLWE, B, tv, tv_per_item);
+}
+
+int tfhe_b200_blind_rotate_extract_batch(tfhe_b200_ctx *c, const uint32_t *in, uint32_t *lv1_out, size_t B) {
+    return run_host(c, -1, nullptr, in, nullptr, lv1_out, Out::LV1, B, nullptr, 0);
+}
+
+int tfhe_b200_keyswitch_batch(tfhe_b200_ctx *c, const uint32_t *lv1, uint32_t *lv0, size_t B) {
+    if (!c || !lv1 || !lv0) return fail(c, TFHE_B200_ERR_INVALID, "null buffer");
+    if (!c->has_ksk) return fail(c, TFHE_B200_ERR_NO_KEY, "no key-switching key loaded");
+    const size_t w0 = (size_t)c->prm.n + 1, w1 = (size_t)kN + 1;
+    const int nd = (int)c->devs.size();
+    for (int k = 0; k < nd; k++) {
+        Device &d = c->devs[k];
+        const size_t lo = B * k / nd, hi = B * (k + 1) / nd;
+        for (size_t off = lo; off < hi; off += c->max_chunk) {
+            const size_t nb = std::min(c->max_chunk, hi - off);
+            CU(c, cudaSetDevice(d.id));
+            if (int r = ensure(c, d.lv1, nb * w1 * 4)) return r;
+            if (int r = ensure(c, d.out, nb * w0 * 4)) return r;
+            CU(c, cudaMemcpyAsync(d.lv1.p, lv1 + off * w1, nb * w1 * 4, cudaMemcpyHostToDevice, d.stream));
+            KsArgs K{(uint32_t *)d.lv1.p, (uint32_t *)d.out.p, d.ksk, (uint32_t)nb, c->prm.n, c->prm.basebit, c->prm.iks_t, c->ksk_pitch};
+            CU(c, launch_keyswitch(K, d.sm_count, d.stream, &c->launches));
+            CU(c, cudaMemcpyAsync(lv0 + off * w0, d.out.p, nb * w0 * 4, cudaMemcpyDeviceToHost, d.stream));
+            CU(c, cudaStreamSynchronize(d.stream));
+        }
+    }
+    return 0;
+}
+
+int tfhe_b200_not_batch(tfhe_b200_ctx *c, const uint32_t *a, uint32_t *out, size_t B) {
+    if (!c || !a || !out) return fail(c, TFHE_B200_ERR_INVALID, "null buffer");
+    if (B == 0) return 0;
+    Device &d = c->devs[0];
+    const size_t bytes = B * ((size_t)c->prm.n + 1) * 4;
+    CU(c, cudaSetDevice(d.id));
+    if (int r = ensure(c, d.a, bytes)) return r;
+    if (int r = ensure(c, d.out, bytes)) return r;
+    CU(c, cudaMemcpyAsync(d.a.p, a, bytes, cudaMemcpyHostToDevice, d.stream));
+    CU(c, launch_negate((uint32_t *)d.a.p, (uint32_t *)d.out.p, bytes / 4, d.stream, &c->launches));
+    CU(c, cudaMemcpyAsync(out, d.out.p, bytes, cudaMemcpyDeviceToHost, d.stream));
+    CU(c, cudaStreamSynchronize(d.stream));
+    return 0;
+}
+
+int tfhe_b200_gate_batch_device(tfhe_b200_ctx *c, int dev, int op, const int32_t *d_ops, const uint32_t *d_a, const uint32_t *d_b,
+                                uint32_t *d_out, size_t B) {
+    if (!c || dev < 0 || dev >= (int)c->devs.size() || !d_a || !d_b || !d_out || (!d_ops && (op < 0 || op > 9)))
+        return fail(c, TFHE_B200_ERR_INVALID, "bad argument");
+    return run_device(c, c->devs[dev], op, d_ops, d_a, d_b, d_out, nullptr, nullptr, B, nullptr, 0);
+}
+
+int tfhe_b200_bootstrap_batch_device(tfhe_b200_ctx *c, int dev, const uint32_t *d_in, uint32_t *d_out, size_t B, const uint32_t *d_tv,
+                                     int tv_per_item) {
+    if (!c || dev < 0 || dev >= (int)c->devs.size() || !d_in || !d_out) return fail(c, TFHE_B200_ERR_INVALID, "bad argument");
+    return run_device(c, c->devs[dev], -1, nullptr, d_in, nullptr, d_out, nullptr, nullptr, B, d_tv, tv_per_item);
+}
+
+int tfhe_b200_blind_rotate_batch_device(tfhe_b200_ctx *c, int dev, const uint32_t *d_in, uint32_t *d_trlwe, size_t B, const uint32_t *d_tv,
+                                        int tv_per_item) {
+    if (!c || dev < 0 || dev >= (int)c->devs.size() || !d_in || !d_trlwe) return fail(c, TFHE_B200_ERR_INVALID, "bad argument");
+    return run_device(c, c->devs[dev], -1, nullptr, d_in, nullptr, nullptr, nullptr, d_trlwe, B, d_tv, tv_per_item);
+}
+
+int tfhe_b200_keyswitch_batch_device(tfhe_b200_ctx *c, int dev, const uint32_t *d_lv1, uint32_t *d_lv0, size_t B) {
+    if (!c || dev < 0 || dev >= (int)c->devs.size() || !d_lv1 || !d_lv0) return fail(c, TFHE_B200_ERR_INVALID, "bad argument");
+    if (!c->has_ksk) return fail(c, TFHE_B200_ERR_NO_KEY, "no key-switching key loaded");
+    Device &d = c->devs[dev];
+    CU(c, cudaSetDevice(d.id));
+    KsArgs K{d_lv1, d_lv0, d.ksk, (uint32_t)B, c->prm.n, c->prm.basebit, c->prm.iks_t, c->ksk_pitch};
+    CU(c, launch_keyswitch(K, d.sm_count, d.stream, &c->launches));
+    return 0;
+}
+
+void *tfhe_b200_stream(tfhe_b200_ctx *c, int dev) {
+    if (!c || dev < 0 || dev >= (int)c->devs.size()) return nullptr;
+    return (void *)c->devs[dev].stream;
+}
+
+int tfhe_b200_sync(tfhe_b200_ctx *c) {
+    if (!c) return TFHE_B200_ERR_INVALID;
+    for (Device &d : c->devs) {
+        CU(c, cudaSetDevice(d.id));
+        CU(c, cudaStreamSynchronize(d.stream));
+    }
+    return 0;
+}
+
+int tfhe_b200_track_margin(tfhe_b200_ctx *c, int enable) {
+    if (!c) return TFHE_B200_ERR_INVALID;
+    c->track_margin = enable != 0;
+    return 0;
+}
+
+double tfhe_b200_max_round_margin(tfhe_b200_ctx *c, int reset) {
+    if (!c) return -1.0;
+    double m = 0.0;
+    for (Device &d : c->devs) {
+        unsigned long long bits = 0;
+        cudaSetDevice(d.id);
+        cudaStreamSynchronize(d.stream);
+        if (cudaMemcpy(&bits, d.margin_bits, 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -1.0;
+        double v;
+        memcpy(&v, &bits, 8);
+        m = std::max(m, v);
+        if (reset) cudaMemset(d.margin_bits, 0, 8);
+    }
+    return m;
+}
+
+uint64_t tfhe_b200_launch_count(const tfhe_b200_ctx *c) { return c ? c->launches : 0; }
+
+int tfhe_b200_set_tuning(tfhe_b200_ctx *c, const char *key, int value) {
+    if (!c || !key) return TFHE_B200_ERR_INVALID;
+    if (!strcmp(key, "kct")) c->tune.kct = value;
+    else if (!strcmp(key, "use_tma")) c->tune.use_tma = value;
+    else if (!strcmp(key, "timing")) c->timing = value != 0;
+    else if (!strcmp(key, "max_chunk")) c->max_chunk = value > 0 ? (size_t)value : c->max_chunk;
+    else return fail(c, TFHE_B200_ERR_INVALID, "unknown tuning key %s", key);
+    return 0;
+}
+
+double tfhe_b200_last_kernel_ms(tfhe_b200_ctx *c, int dev, int which) {
+    if (!c || dev < 0 || dev >= (int)c->devs.size() || which < 0 || which > 1) return -1.0;
+    Device &d = c->devs[dev];
+    if (!d.ev_valid || cudaSetDevice(d.id) != cudaSuccess || cudaEventSynchronize(d.ev[2]) != cudaSuccess) return -1.0;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, d.ev[which], d.ev[which + 1]) != cudaSuccess) return -1.0;
+    return (double)ms;
+}
+
+double tfhe_b200_measure_fp64_tflops(tfhe_b200_ctx *c, int dev) {
+    if (!c || dev < 0 || dev >= (int)c->devs.size()) return -1.0;
+    Device &d = c->devs[dev];
+    if (cudaSetDevice(d.id) != cudaSuccess) return -1.0;
+    double tf = 0.0;
+    if (run_fp64_peak(d.sm_count, d.stream, &tf, &c->launches) != cudaSuccess) return -1.0;
+    return tf;
+}
+
+}  // extern "C"
+
+// exact mode is provided by blind_rotate_exact.cu

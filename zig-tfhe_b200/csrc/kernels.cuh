@@ -1,0 +1,61 @@
+// kernels.cuh -- launch interfaces of the device kernels (internal to libtfhe_b200).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "negacyclic_fft.cuh"
+
+namespace tfhe_b200 {
+
+// Arguments of the blind-rotation kernel K1 (one 64-thread group per ciphertext).
+struct BrArgs {
+    const uint32_t *in_a;   // [B][n+1]: first gate operand, or the ciphertext itself when op < 0
+    const uint32_t *in_b;   // [B][n+1]: second gate operand (ignored when the opcode is < 0)
+    const int32_t *ops;     // per-item opcode, or nullptr -> `op`
+    int op;                 // tfhe_b200_gate, or -1 = plain bootstrap input (no linear part)
+    const cplx *bsk;        // device layout: [n*2L] chunks of [ab][q0][t] cplx (16 KiB each)
+    const cplx *tw2;        // [7][8]
+    const cplx *tw3;        // [7][64]
+    const uint32_t *testvec;  // nullptr -> (a = 0, b = 2^29); else [2][N] or [B][2][N]
+    int tv_per_item;
+    uint32_t *out_lv1;      // [B][N+1] sampleExtractIndex(.,0), or nullptr
+    uint32_t *out_trlwe;    // [B][2][N] accumulator, or nullptr
+    unsigned long long *margin_bits;  // global max |t-round(t)| as double bits (MARGIN variant), or nullptr
+    uint32_t B;
+    int n, L, bgbit;
+    uint32_t offset;        // CloudKey.decomposition_offset
+    int wide_round;         // 1: F2I.S64 rounding (large-digit sets), 0: magic-add rounding
+};
+
+struct BrTuning {
+    int kct = 0;        // ciphertexts per CTA (0 = default)
+    int use_tma = 1;    // stream key chunks with cp.async.bulk + mbarrier (0: direct global loads)
+};
+
+// returns cudaSuccess or the launch error; *launches += kernels launched
+cudaError_t launch_blind_rotate(const BrArgs &a, const BrTuning &tune, bool track_margin, cudaStream_t s, uint64_t *launches);
+cudaError_t launch_blind_rotate_exact(const BrArgs &a, const double *exact_tables, cudaStream_t s, uint64_t *launches);
+
+// K2: identity key switching, lv1 [B][N+1] -> lv0 [B][n+1].  ksk_dev: [N][t][base-1][pitch] u32.
+struct KsArgs {
+    const uint32_t *lv1;
+    uint32_t *lv0;
+    const uint32_t *ksk;
+    uint32_t B;
+    int n, basebit, iks_t, pitch;   // pitch = row length in u32 (multiple of 4)
+};
+cudaError_t launch_keyswitch(const KsArgs &a, int sm_count, cudaStream_t s, uint64_t *launches);
+
+// one-time key re-layout kernels
+cudaError_t launch_permute_bsk(const double *ref_bsk, cplx *out, int n, int L, cudaStream_t s, uint64_t *launches);
+cudaError_t launch_repack_ksk(const uint32_t *ref_ksk, size_t ref_row_stride_u32, uint32_t *out, int n, int basebit, int iks_t,
+                              int pitch, cudaStream_t s, uint64_t *launches);
+// K3: out = -a over [B][n+1]
+cudaError_t launch_negate(const uint32_t *a, uint32_t *out, size_t count, cudaStream_t s, uint64_t *launches);
+// first n entries + body of an lv1 sample -> TLWELv0-shaped "hybrid" sample (trlwe.zig:165-180)
+cudaError_t launch_extract2(const uint32_t *lv1, uint32_t *out, uint32_t B, int n, cudaStream_t s, uint64_t *launches);
+
+// FP64 FMA throughput microbenchmark (roofline denominator): returns seconds for `flops_out` flops
+cudaError_t run_fp64_peak(int sm_count, cudaStream_t s, double *tflops, uint64_t *launches);
+
+}  // namespace tfhe_b200

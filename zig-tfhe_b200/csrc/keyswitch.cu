@@ -1,0 +1,196 @@
+// keyswitch.cu -- K2: batched identity key switching lv1 -> lv0 (integer, bit-exact on any schedule).
+//
+// Replaces trgsw.identityKeySwitching (src/trgsw.zig:471-502):
+//   res.b = src.b;  for i < N, j < t:  k = digit_j(src.a[i] + prec_offset);  if k != 0: res -= KSK[i][j][k]
+// u32 wrapping subtraction is associative and commutative, so any tiling / split / atomic order gives
+// the reference's bits.
+//
+// Tiling: one CTA owns CT ciphertexts x all n+1 output columns (each thread 4 columns, CT uint4
+// accumulators in registers) and walks a slice of the (i, j) pairs.  For every pair the base-1 key rows
+// are loaded once (coalesced 16-byte loads) and applied to all CT ciphertexts, so key traffic is
+// 1/CT of the per-ciphertext gather (19.4 MB/ciphertext at the 128-bit set).  Small batches split the
+// i range over several CTAs and combine with u32 atomics so the grid still fills the 148 SMs.
+//
+// Device key layout (built by repack_ksk_kernel): [N][t][base-1][pitch] u32, pitch = roundup4(n+1);
+// the never-read k = 0 rows of the reference layout (src/key.zig:158-161) are dropped.
+#include <cuda_runtime.h>
+
+#include "kernels.cuh"
+
+namespace tfhe_b200 {
+
+namespace {
+
+__device__ __forceinline__ void sub4(uint4 &a, const uint4 &r) {
+    a.x -= r.x; a.y -= r.y; a.z -= r.z; a.w -= r.w;
+}
+
+// BASEBIT = 2 fast path (80/110/128-bit and UINT1 sets): 3 rows per (i,j) held in registers.
+// BASEBIT = 0: generic base, row fetched per ciphertext.
+template <int CT, int BASEBIT>
+__global__ void __launch_bounds__(320) keyswitch_kernel(const KsArgs P, int i_per_split, int use_atomics) {
+    extern __shared__ uint32_t abar[];   // [CT][i_per_split]
+    const int n = P.n, t = P.iks_t;
+    const int basebit = BASEBIT ? BASEBIT : P.basebit;
+    const int rows_per_pair = (1 << basebit) - 1;
+    const int pitch4 = P.pitch >> 2;
+    const int col = threadIdx.x;                       // uint4 column
+    const size_t ct0 = (size_t)blockIdx.x * CT;
+    const int i0 = blockIdx.y * i_per_split;
+    const int i1 = min(kN, i0 + i_per_split);
+    const uint32_t prec_offset = 1u << (32 - (1 + basebit * t));   // trgsw.zig:483
+    const uint32_t kmask = (1u << basebit) - 1u;
+
+    for (int idx = threadIdx.x; idx < CT * (i1 - i0); idx += blockDim.x) {
+        const int c = idx / (i1 - i0), i = idx - c * (i1 - i0);
+        const size_t ct = ct0 + c;
+        // inactive slots: abar = 0 -> every digit is 0 -> nothing subtracted
+        abar[c * i_per_split + i] = (ct < P.B) ? P.lv1[ct * (size_t)(kN + 1) + i0 + i] + prec_offset : 0u;
+    }
+    __syncthreads();
+    if (col >= pitch4) return;
+
+    uint4 acc[CT];
+#pragma unroll
+    for (int c = 0; c < CT; c++) acc[c] = make_uint4(0u, 0u, 0u, 0u);
+
+    const uint4 *ksk4 = reinterpret_cast<const uint4 *>(P.ksk);
+    for (int i = i0; i < i1; i++) {
+        uint32_t ab[CT];
+#pragma unroll
+        for (int c = 0; c < CT; c++) ab[c] = abar[c * i_per_split + (i - i0)];
+        const uint4 *rowp = ksk4 + ((size_t)i * t) * rows_per_pair * pitch4 + col;
+        for (int j = 0; j < t; j++, rowp += (size_t)rows_per_pair * pitch4) {
+            const int sh = 32 - (j + 1) * basebit;
+            if (BASEBIT == 2) {
+                const uint4 r1 = __ldg(rowp), r2 = __ldg(rowp + pitch4), r3 = __ldg(rowp + 2 * pitch4);
+#pragma unroll
+                for (int c = 0; c < CT; c++) {
+                    const uint32_t k = (ab[c] >> sh) & 3u;     // warp-uniform
+                    if (k == 1u) sub4(acc[c], r1);
+                    else if (k == 2u) sub4(acc[c], r2);
+                    else if (k == 3u) sub4(acc[c], r3);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < CT; c++) {
+                    const uint32_t k = (ab[c] >> sh) & kmask;
+                    if (k != 0u) sub4(acc[c], __ldg(rowp + (size_t)(k - 1u) * pitch4));
+                }
+            }
+        }
+    }
+
+    // write back: column n additionally receives src.b (trgsw.zig:481), added by the first split only
+#pragma unroll
+    for (int c = 0; c < CT; c++) {
+        const size_t ct = ct0 + c;
+        if (ct >= P.B) break;
+        uint32_t vals[4] = {acc[c].x, acc[c].y, acc[c].z, acc[c].w};
+        uint32_t *o = P.lv0 + ct * (size_t)(n + 1);
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int x = col * 4 + e;
+            if (x > n) continue;
+            uint32_t v = vals[e];
+            if (x == n && blockIdx.y == 0) v += P.lv1[ct * (size_t)(kN + 1) + kN];
+            if (use_atomics) atomicAdd(&o[x], v);
+            else o[x] = v;
+        }
+    }
+}
+
+template <int CT>
+cudaError_t launch_ct(const KsArgs &a, int splits, cudaStream_t s) {
+    const int i_per_split = (kN + splits - 1) / splits;
+    const size_t smem = (size_t)CT * i_per_split * sizeof(uint32_t);
+    const dim3 grid((a.B + CT - 1) / CT, splits);
+    const int threads = (((a.pitch >> 2) + 31) / 32) * 32;
+    cudaError_t e;
+    if (a.basebit == 2) {
+        auto k = keyswitch_kernel<CT, 2>;
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k<<<grid, threads, smem, s>>>(a, i_per_split, splits > 1);
+    } else {
+        auto k = keyswitch_kernel<CT, 0>;
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k<<<grid, threads, smem, s>>>(a, i_per_split, splits > 1);
+    }
+    return cudaGetLastError();
+}
+
+__global__ void repack_ksk_kernel(const uint32_t *ref, size_t ref_stride, uint32_t *out, int n, int base, int pairs, int pitch) {
+    // one block per (i,j) pair, rows k = 1..base-1
+    const int pair = blockIdx.x;
+    if (pair >= pairs) return;
+    for (int k = 1; k < base; k++) {
+        const uint32_t *src = ref + ((size_t)pair * base + k) * ref_stride;
+        uint32_t *dst = out + ((size_t)pair * (base - 1) + (k - 1)) * pitch;
+        for (int x = threadIdx.x; x < pitch; x += blockDim.x) dst[x] = (x <= n) ? src[x] : 0u;
+    }
+}
+
+__global__ void negate_kernel(const uint32_t *a, uint32_t *out, size_t count) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = 0u - a[i];
+}
+
+__global__ void extract2_kernel(const uint32_t *lv1, uint32_t *out, uint32_t B, int n) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t w = (size_t)n + 1;
+    if (idx >= (size_t)B * w) return;
+    const size_t ct = idx / w;
+    const int x = (int)(idx - ct * w);
+    // sampleExtractIndex2(., 0): first n mask entries + body (trlwe.zig:165-180)
+    out[idx] = (x == n) ? lv1[ct * (size_t)(kN + 1) + kN] : lv1[ct * (size_t)(kN + 1) + x];
+}
+
+}  // namespace
+
+cudaError_t launch_keyswitch(const KsArgs &a, int sm_count, cudaStream_t s, uint64_t *launches) {
+    if (a.B == 0) return cudaSuccess;
+    if (a.pitch > 320 * 4) return cudaErrorInvalidValue;
+    // pick the tile so the grid fills the machine; split the i range for small batches
+    int ct = (a.B >= (uint32_t)(16 * sm_count)) ? 16 : (a.B >= (uint32_t)(8 * sm_count)) ? 8 : 4;
+    const int tiles = (a.B + ct - 1) / ct;
+    int splits = 1;
+    while (tiles * splits < 2 * sm_count && splits < 32) splits *= 2;
+    cudaError_t e;
+    if (splits > 1) {
+        e = cudaMemsetAsync(a.lv0, 0, (size_t)a.B * (a.n + 1) * sizeof(uint32_t), s);
+        if (e != cudaSuccess) return e;
+    }
+    if (launches) (*launches)++;
+    switch (ct) {
+        case 16: return launch_ct<16>(a, splits, s);
+        case 8: return launch_ct<8>(a, splits, s);
+        default: return launch_ct<4>(a, splits, s);
+    }
+}
+
+cudaError_t launch_repack_ksk(const uint32_t *ref_ksk, size_t ref_row_stride_u32, uint32_t *out, int n, int basebit, int iks_t,
+                              int pitch, cudaStream_t s, uint64_t *launches) {
+    const int pairs = kN * iks_t;
+    repack_ksk_kernel<<<pairs, 256, 0, s>>>(ref_ksk, ref_row_stride_u32, out, n, 1 << basebit, pairs, pitch);
+    if (launches) (*launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_negate(const uint32_t *a, uint32_t *out, size_t count, cudaStream_t s, uint64_t *launches) {
+    if (!count) return cudaSuccess;
+    negate_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(a, out, count);
+    if (launches) (*launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_extract2(const uint32_t *lv1, uint32_t *out, uint32_t B, int n, cudaStream_t s, uint64_t *launches) {
+    if (!B) return cudaSuccess;
+    const size_t total = (size_t)B * (n + 1);
+    extract2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(lv1, out, B, n);
+    if (launches) (*launches)++;
+    return cudaGetLastError();
+}
+
+}  // namespace tfhe_b200
