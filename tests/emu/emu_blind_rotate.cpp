@@ -20,7 +20,7 @@ namespace {
 
 struct Group {
     uint32_t acc_a[kN], acc_b[kN];
-    cplx x1[512], x2[512];
+    cplx x1[kX1Slots], x2[kX2Slots];
     cplx tw2[kTw2Len], tw3[kTw3Len];
     Group() { make_twiddle_tables(tw2, tw3); }
 };
@@ -138,8 +138,8 @@ void emu_blind_rotate(int n, int L, int bgbit, uint32_t offset, const uint32_t *
         const int u = (j - btil) & (2 * kN - 1);
         const uint32_t va = testvec ? testvec[u & (kN - 1)] : 0u;
         const uint32_t vb = testvec ? testvec[kN + (u & (kN - 1))] : 0x20000000u;
-        G.acc_a[j] = (u & kN) ? 0u - va : va;
-        G.acc_b[j] = (u & kN) ? 0u - vb : vb;
+        G.acc_a[acc_pos(j)] = (u & kN) ? 0u - va : va;   // accumulators live in acc_pos order, like the kernel's
+        G.acc_b[acc_pos(j)] = (u & kN) ? 0u - vb : vb;
     }
     double margin = 0.0;
     static cplx v[64][8], oa[64][8], ob[64][8];
@@ -166,9 +166,8 @@ void emu_blind_rotate(int n, int L, int bgbit, uint32_t offset, const uint32_t *
             uint32_t *accp = h ? G.acc_b : G.acc_a;
             inv_all(G, o);
             for (int t = 0; t < 64; t++) {
-                const int hi = t >> 3, lo = t & 7;
                 for (int p = 0; p < 8; p++) {
-                    const int e = 64 * p + 8 * lo + hi;
+                    const int e = 64 * p + t;   // acc_pos of coefficient 64 p + 8 lo + hi
                     const double xr = o[t][p].re, xi = o[t][p].im;
                     margin = std::fmax(margin, std::fabs(xr - std::nearbyint(xr)));
                     margin = std::fmax(margin, std::fabs(xi - std::nearbyint(xi)));
@@ -177,13 +176,16 @@ void emu_blind_rotate(int n, int L, int bgbit, uint32_t offset, const uint32_t *
                 }
             }
         }
-        if (trace) {
-            std::memcpy(trace + (size_t)i * 2 * kN, G.acc_a, sizeof(G.acc_a));
-            std::memcpy(trace + (size_t)i * 2 * kN + kN, G.acc_b, sizeof(G.acc_b));
-        }
+        if (trace)
+            for (int j = 0; j < kN; j++) {
+                trace[(size_t)i * 2 * kN + j] = G.acc_a[acc_pos(j)];
+                trace[(size_t)i * 2 * kN + kN + j] = G.acc_b[acc_pos(j)];
+            }
     }
-    std::memcpy(out_trlwe, G.acc_a, sizeof(G.acc_a));
-    std::memcpy(out_trlwe + kN, G.acc_b, sizeof(G.acc_b));
+    for (int j = 0; j < kN; j++) {
+        out_trlwe[j] = G.acc_a[acc_pos(j)];
+        out_trlwe[kN + j] = G.acc_b[acc_pos(j)];
+    }
     if (margin_out) *margin_out = margin;
 }
 

@@ -10,7 +10,10 @@
 //       ifft1024 x 2L, fmaInFd1024, fft1024 x 2   src/fft.zig:293-443, src/trgsw.zig:157-189
 //   trlwe.sampleExtractIndex(., 0)      src/trlwe.zig:146-162  (fused epilogue)
 //
-// Execution model.  One CTA = KCT groups of 64 threads (KCT = 6: 12 warps, 3 per SM sub-partition, 168 registers).  A group owns one
+// Execution model.  One CTA = KCT groups of 64 threads.  Default KCT = 4: 8 warps, 2 per SM sub-partition, so the
+// per-thread twiddles of passes 2 and 3 live in registers (252-register budget) instead of being re-read from
+// shared memory (the shared-memory data pipe is this kernel's limiter, profiles/r01_ncu_k1_v1_summary.txt).
+// KCT = 5, 6 keep the twiddle tables in shared memory (168 registers).  A group owns one
 // ciphertext for all n iterations: its TRLWE accumulator (2 x 1024 u32) never leaves shared memory,
 // the 2L digit spectra never leave registers (each is consumed by the pointwise MAC as soon as its
 // last radix-8 pass finishes), and the two output spectra are 16 complex accumulators per thread.
@@ -117,40 +120,55 @@ __device__ __forceinline__ uint32_t gate_constant(int op) {
     }
 }
 
-// forward transform, role A registers in -> role C (leaf order) out.  2 named barriers + 1 warp sync.
-template <bool USE_TMA>
-__device__ __forceinline__ void fwd_transform(cplx (&v)[8], cplx *x1, cplx *x2, const cplx *tw2s, const cplx *tw3s, int t,
-                                              int hi, int lo, int barid, Producer &pr) {
+// Per-group exchange state.  X2 is double-buffered when DBX2 (one named barrier per transform instead
+// of two): a writer of buffer b at transform k has passed the barrier of transform k-1, which every
+// reader of b at transform k-2 reached only after finishing its reads.
+struct Xbuf {
+    cplx *x1;
+    cplx *x2;     // two consecutive buffers of kX2Slots when double-buffered
+    int flip;     // 0 or kX2Slots
+};
+
+// forward transform, role A registers in -> role C (leaf order) out
+template <bool USE_TMA, bool DBX2>
+__device__ __forceinline__ void fwd_transform(cplx (&v)[8], Xbuf &xb, const cplx *tw2, int tw2_stride, const cplx *tw3,
+                                              int tw3_stride, int hi, int lo, int barid, Producer &pr) {
     fwd_pass1(v);
+    cplx *x1 = xb.x1;
 #pragma unroll
     for (int q = 0; q < 8; q++) x1[x1_slot(hi, q, lo)] = v[q];
     __syncwarp();
 #pragma unroll
     for (int q = 0; q < 8; q++) v[q] = x1[x1_slot(hi, lo, q)];
-    fwd_pass(v, tw2s + lo, 8);
+    fwd_pass(v, tw2, tw2_stride);
     if (USE_TMA) producer_poll(pr);
-    bar_sync(barid, kGroupThreads);  // every reader of the previous X2 contents is done
+    cplx *x2 = xb.x2 + (DBX2 ? xb.flip : 0);
+    if (DBX2) xb.flip ^= kX2Slots;
+    else bar_sync(barid, kGroupThreads);   // every reader of the previous X2 contents is done
 #pragma unroll
     for (int q = 0; q < 8; q++) x2[x2_slot(lo, q, hi)] = v[q];
     bar_sync(barid, kGroupThreads);
 #pragma unroll
     for (int q = 0; q < 8; q++) v[q] = x2[x2_slot(hi, lo, q)];
-    fwd_pass(v, tw3s + t, 64);
+    fwd_pass(v, tw3, tw3_stride);
 }
 
 // inverse transform, role C (leaf order) in -> role A out: v[p] = c_e, e = 64 p + 8 lo + hi
-template <bool USE_TMA>
-__device__ __forceinline__ void inv_transform(cplx (&v)[8], cplx *x1, cplx *x2, const cplx *tw2s, const cplx *tw3s, int t,
-                                              int hi, int lo, int barid, Producer &pr) {
-    inv_pass(v, tw3s + t, 64);
+template <bool USE_TMA, bool DBX2>
+__device__ __forceinline__ void inv_transform(cplx (&v)[8], Xbuf &xb, const cplx *tw2, int tw2_stride, const cplx *tw3,
+                                              int tw3_stride, int hi, int lo, int barid, Producer &pr) {
+    inv_pass(v, tw3, tw3_stride);
     if (USE_TMA) producer_poll(pr);
-    bar_sync(barid, kGroupThreads);
+    cplx *x2 = xb.x2 + (DBX2 ? xb.flip : 0);
+    if (DBX2) xb.flip ^= kX2Slots;
+    else bar_sync(barid, kGroupThreads);
 #pragma unroll
     for (int q = 0; q < 8; q++) x2[x2_slot(hi, lo, q)] = v[q];
     bar_sync(barid, kGroupThreads);
 #pragma unroll
     for (int q = 0; q < 8; q++) v[q] = x2[x2_slot(lo, q, hi)];
-    inv_pass(v, tw2s + lo, 8);
+    inv_pass(v, tw2, tw2_stride);
+    cplx *x1 = xb.x1;
 #pragma unroll
     for (int q = 0; q < 8; q++) x1[x1_slot(hi, lo, q)] = v[q];
     __syncwarp();
@@ -160,10 +178,10 @@ __device__ __forceinline__ void inv_transform(cplx (&v)[8], cplx *x1, cplx *x2, 
 }
 
 template <bool MARGIN>
-__device__ __forceinline__ void round_accumulate(const cplx (&v)[8], uint32_t *accp, int hi, int lo, int wide, double &margin) {
+__device__ __forceinline__ void round_accumulate(const cplx (&v)[8], uint32_t *accp, int t, int wide, double &margin) {
 #pragma unroll
     for (int p = 0; p < 8; p++) {
-        const int e = 64 * p + 8 * lo + hi;
+        const int e = 64 * p + t;   // acc_pos of coefficient 64 p + 8 lo + hi
         if (MARGIN) {
             margin = fmax(margin, fabs(v[p].re - rint(v[p].re)));
             margin = fmax(margin, fabs(v[p].im - rint(v[p].im)));
@@ -177,29 +195,47 @@ __device__ __forceinline__ void round_accumulate(const cplx (&v)[8], uint32_t *a
 
 __host__ __device__ constexpr int align16(int x) { return (x + 15) & ~15; }
 
+// shared-memory footprint of one ciphertext group
+template <int KCT>
+struct Layout {
+    static constexpr bool kTwRegs = KCT <= 4;   // pass-2 twiddles in registers (252-register budget)
+    static constexpr bool kTw3Regs = true;      // pass-3 twiddles in registers (fits the 168-register budget too)
+    static constexpr bool kDbX2 = KCT <= 4;     // double-buffered X2 (fits when only 4 groups share the SM)
+    static constexpr int kAccBytes = 2 * kN * 4;
+    static constexpr int kX1Bytes = kX1Slots * 16;
+    static constexpr int kX2Bytes = kX2Slots * 16;
+    __host__ __device__ static constexpr int group_bytes(int n) {
+        return kAccBytes + kX1Bytes + (kDbX2 ? 2 : 1) * kX2Bytes + align16((n + 1) * 2);
+    }
+    __host__ __device__ static constexpr int table_bytes() { return (kTw3Regs ? 0 : kTw3Len * 16) + (kTwRegs ? 0 : kTw2Len * 16); }
+};
+
 template <int KCT, bool USE_TMA, bool MARGIN>
 __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(const BrArgs P) {
+    using Lay = Layout<KCT>;
+    constexpr bool TWREG = Lay::kTwRegs, TW3REG = Lay::kTw3Regs, DBX2 = Lay::kDbX2;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // ---- carve shared memory
     unsigned char *ptr = smem_raw;
     cplx *bsk_ring = reinterpret_cast<cplx *>(ptr);
     if (USE_TMA) ptr += kStages * kBskChunkBytes;
     cplx *tw3s = reinterpret_cast<cplx *>(ptr);
-    ptr += kTw3Len * sizeof(cplx);
-    cplx *tw2s = reinterpret_cast<cplx *>(ptr);
-    ptr += kTw2Len * sizeof(cplx);
+    cplx *tw2s = tw3s + (TW3REG ? 0 : kTw3Len);
+    ptr += Lay::table_bytes();
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(ptr);
     uint64_t *empty_bar = full_bar + kStages;
-    ptr += 2 * kStages * sizeof(uint64_t) + 16;
+    ptr += 64;
     const int n = P.n, L = P.L, bgbit = P.bgbit;
-    const int group_bytes = 3 * 8192 + align16((n + 1) * 2);
+    const int group_bytes = Lay::group_bytes(n);
 
     const int tid = threadIdx.x;
     const int first_ct = blockIdx.x * KCT;
     const int n_active = min(KCT, (int)P.B - first_ct);
 
-    for (int i = tid; i < kTw3Len; i += blockDim.x) tw3s[i] = P.tw3[i];
-    for (int i = tid; i < kTw2Len; i += blockDim.x) tw2s[i] = P.tw2[i];
+    if (!TW3REG)
+        for (int i = tid; i < kTw3Len; i += blockDim.x) tw3s[i] = P.tw3[i];
+    if (!TWREG)
+        for (int i = tid; i < kTw2Len; i += blockDim.x) tw2s[i] = P.tw2[i];
     if (USE_TMA && tid == 0) {
         for (int s = 0; s < kStages; s++) {
             mbar_init(&full_bar[s], 1);
@@ -217,10 +253,23 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
     unsigned char *gb = ptr + (size_t)g * group_bytes;
     uint32_t *acc_a = reinterpret_cast<uint32_t *>(gb);
     uint32_t *acc_b = acc_a + kN;
-    cplx *x1 = reinterpret_cast<cplx *>(gb + 8192);
-    cplx *x2 = reinterpret_cast<cplx *>(gb + 16384);
-    uint16_t *atil = reinterpret_cast<uint16_t *>(gb + 24576);
+    Xbuf xb;
+    xb.x1 = reinterpret_cast<cplx *>(gb + Lay::kAccBytes);
+    xb.x2 = reinterpret_cast<cplx *>(gb + Lay::kAccBytes + Lay::kX1Bytes);
+    xb.flip = 0;
+    uint16_t *atil = reinterpret_cast<uint16_t *>(gb + Lay::kAccBytes + Lay::kX1Bytes + (DBX2 ? 2 : 1) * Lay::kX2Bytes);
     const size_t ct = (size_t)first_ct + g;
+
+    // per-thread twiddles: role B node q2 = lo, role C node t (register-resident when TWREG)
+    cplx tw2r[7], tw3r[7];
+#pragma unroll
+    for (int p = 1; p < 8; p++) {
+        if (TWREG) tw2r[p - 1] = P.tw2[tw2_index(p, lo)];
+        if (TW3REG) tw3r[p - 1] = P.tw3[tw3_index(p, t)];
+    }
+    const cplx *tw2 = TWREG ? tw2r : tw2s + lo;
+    const cplx *tw3 = TW3REG ? tw3r : tw3s + t;
+    constexpr int tw2_stride = TWREG ? 1 : 8, tw3_stride = TW3REG ? 1 : 64;
 
     // ---- prologue: gate linear part (gates.zig:48-121) + modulus switch (trgsw.zig:297,312)
     {
@@ -235,7 +284,7 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
         }
     }
     bar_sync(barid, kGroupThreads);
-    // ---- acc = X^btil * testvec (trgsw.zig:300-306)
+    // ---- acc = X^btil * testvec (trgsw.zig:300-306), stored in acc_pos order
     {
         const int btil = atil[n];
         const uint32_t *tv = P.testvec ? P.testvec + (P.tv_per_item ? ct * (size_t)(2 * kN) : 0) : nullptr;
@@ -243,8 +292,8 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
             const int u = (j - btil) & (2 * kN - 1);
             const uint32_t va = tv ? tv[u & (kN - 1)] : 0u;
             const uint32_t vb = tv ? tv[kN + (u & (kN - 1))] : 0x20000000u;   // key.zig:134-145
-            acc_a[j] = (u & kN) ? 0u - va : va;
-            acc_b[j] = (u & kN) ? 0u - vb : vb;
+            acc_a[acc_pos(j)] = (u & kN) ? 0u - va : va;
+            acc_b[acc_pos(j)] = (u & kN) ? 0u - vb : vb;
         }
     }
     bar_sync(barid, kGroupThreads);
@@ -277,7 +326,7 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
             for (int l = 0; l < L; l++) {
                 cplx v[8];
                 digits_to_cplx(v, d, 32 - (l + 1) * bgbit, mask, half_bg);
-                fwd_transform<USE_TMA>(v, x1, x2, tw2s, tw3s, t, hi, lo, barid, pr);
+                fwd_transform<USE_TMA, DBX2>(v, xb, tw2, tw2_stride, tw3, tw3_stride, hi, lo, barid, pr);
                 const cplx *chunk;
                 if (USE_TMA) {
                     while (!mbar_try_wait(&full_bar[stage], phase)) producer_poll(pr);
@@ -297,22 +346,22 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
                 }
             }
         }
-        inv_transform<USE_TMA>(oa, x1, x2, tw2s, tw3s, t, hi, lo, barid, pr);
-        round_accumulate<MARGIN>(oa, acc_a, hi, lo, wide, margin);
-        inv_transform<USE_TMA>(ob, x1, x2, tw2s, tw3s, t, hi, lo, barid, pr);
-        round_accumulate<MARGIN>(ob, acc_b, hi, lo, wide, margin);
+        inv_transform<USE_TMA, DBX2>(oa, xb, tw2, tw2_stride, tw3, tw3_stride, hi, lo, barid, pr);
+        round_accumulate<MARGIN>(oa, acc_a, t, wide, margin);
+        inv_transform<USE_TMA, DBX2>(ob, xb, tw2, tw2_stride, tw3, tw3_stride, hi, lo, barid, pr);
+        round_accumulate<MARGIN>(ob, acc_b, t, wide, margin);
         bar_sync(barid, kGroupThreads);   // accumulator complete before the next rotated reads
     }
 
     // ---- epilogue
     if (P.out_trlwe) {
         uint32_t *o = P.out_trlwe + ct * (size_t)(2 * kN);
-        for (int j = t; j < kN; j += kGroupThreads) { o[j] = acc_a[j]; o[kN + j] = acc_b[j]; }
+        for (int j = t; j < kN; j += kGroupThreads) { o[j] = acc_a[acc_pos(j)]; o[kN + j] = acc_b[acc_pos(j)]; }
     }
     if (P.out_lv1) {   // sampleExtractIndex(., 0): trlwe.zig:146-162
         uint32_t *o = P.out_lv1 + ct * (size_t)(kN + 1);
         for (int j = t; j <= kN; j += kGroupThreads)
-            o[j] = (j == 0) ? acc_a[0] : (j == kN) ? acc_b[0] : 0u - acc_a[kN - j];
+            o[j] = (j == 0) ? acc_a[0] : (j == kN) ? acc_b[0] : 0u - acc_a[acc_pos(kN - j)];
     }
     if (MARGIN && P.margin_bits) {
 #pragma unroll
@@ -323,9 +372,9 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
 
 template <int KCT, bool USE_TMA, bool MARGIN>
 cudaError_t launch_variant(const BrArgs &a, cudaStream_t s) {
+    using Lay = Layout<KCT>;
     const int threads = KCT * kGroupThreads;
-    const size_t smem = (USE_TMA ? kStages * kBskChunkBytes : 0) + (kTw3Len + kTw2Len) * sizeof(cplx) + 2 * kStages * 8 + 16 +
-                        (size_t)KCT * (3 * 8192 + align16((a.n + 1) * 2));
+    const size_t smem = (USE_TMA ? kStages * kBskChunkBytes : 0) + Lay::table_bytes() + 64 + (size_t)KCT * Lay::group_bytes(a.n);
     auto kern = blind_rotate_kernel<KCT, USE_TMA, MARGIN>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -345,7 +394,7 @@ cudaError_t launch_kct(const BrArgs &a, bool tma, bool margin, cudaStream_t s) {
 cudaError_t launch_blind_rotate(const BrArgs &a, const BrTuning &tune, bool track_margin, cudaStream_t s, uint64_t *launches) {
     if (a.B == 0) return cudaSuccess;
     int kct = tune.kct;
-    if (kct <= 0) kct = (a.B >= 148u * 6u) ? 6 : (a.B >= 148u * 4u) ? 4 : (a.B >= 148u * 2u) ? 2 : 1;
+    if (kct <= 0) kct = (a.B >= 148u * 4u) ? 4 : (a.B >= 148u * 2u) ? 2 : 1;
     if (launches) (*launches)++;
     switch (kct) {
         case 1: return launch_kct<1>(a, tune.use_tma != 0, track_margin, s);

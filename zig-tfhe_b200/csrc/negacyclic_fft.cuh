@@ -24,7 +24,9 @@
 //   role B (passes 2 / 2'):  t = 8 k0 + q2, registers hold k1 = 0..7   (after pass 2: q1 = 0..7)
 //   role C (passes 3 / 3'):  t = 8 q2 + q1, registers hold k0 = 0..7   (after pass 3: q0 = 0..7)
 // A<->B is a transpose inside one quarter-warp (exchange X1), B<->C crosses the two warps (X2).
-// Both go through XOR-swizzled shared memory (16-byte slots, conflict-free for LDS/STS.128).
+// Both go through padded shared-memory buffers (16-byte slots, row pitches 9 / 73 slots): every
+// access is base + compile-time constant, and each quarter-warp touches 8 distinct 16-byte columns,
+// so LDS/STS.128 are conflict-free with zero address arithmetic in the loop.
 //
 // All floating-point contractions are explicit (fma()), and the translation units are compiled
 // with --fmad=false / -ffp-contract=off, so the host emulator in tests/ replays the device
@@ -175,11 +177,21 @@ TFHE_HD void inv_pass1(cplx (&v)[8]) {
     for (int p = 1; p < 8; p++) v[p] = cmulc(v[p], tw1(p));
 }
 
-// ---- shared-memory exchange slots (units of one cplx = 16 bytes, 512 slots per buffer) ----
-// X1: role A (k0,k1) element q2  <->  role B (k0,q2) element k1
-TFHE_HD int x1_slot(int k0, int q2, int k1) { return k0 * 64 + q2 * 8 + (k1 ^ q2); }
-// X2: role B (k0,q2) element q1  <->  role C (q2,q1) element k0
-TFHE_HD int x2_slot(int q2, int q1, int k0) { return q2 * 64 + q1 * 8 + (k0 ^ q1 ^ q2); }
+// ---- shared-memory exchange slots (units of one cplx = 16 bytes) ----
+// X1: role A (k0,k1) element q2  <->  role B (k0,q2) element k1.   Lanes of a quarter-warp differ in
+// k1 (writes, stride 1) or q2 (reads, stride 9 = 1 mod 8).
+constexpr int kX1Slots = 8 * 72;
+TFHE_HD int x1_slot(int k0, int q2, int k1) { return k0 * 72 + q2 * 9 + k1; }
+// X2: role B (k0,q2) element q1  <->  role C (q2,q1) element k0.   Writes: lanes differ in q2
+// (stride 73 = 1 mod 8); reads: lanes differ in q1 (stride 9).
+constexpr int kX2Slots = 7 * 73 + 7 * 9 + 8;
+TFHE_HD int x2_slot(int q2, int q1, int k0) { return q2 * 73 + q1 * 9 + k0; }
+
+// ---- accumulator layout in shared memory ----
+// Coefficient e of a polynomial lives at acc_pos(e): the two low 3-bit fields of e are swapped, so the
+// 16 coefficients e = 64 p + 8 k1 + k0 (p = 0..15) that role-A thread t = 8 k0 + k1 owns sit at
+// 64 p + t (conflict-free, constant offsets), and a rotated read (e - atil) is conflict-free as well.
+TFHE_HD int acc_pos(int e) { return (e & ~63) | ((e & 7) << 3) | ((e >> 3) & 7); }
 
 // twiddle table layouts (shared memory / global): tw2[p-1][q2], tw3[p-1][t] with t = 8 q2 + q1
 TFHE_HD int tw2_index(int p, int q2) { return (p - 1) * 8 + q2; }
@@ -195,19 +207,20 @@ constexpr int kBskChunkBytes = kBskChunkCplx * 16;
 TFHE_HD int leaf_to_ref_bin(int q2, int q1, int q0) { return (512 - (q2 + 8 * q1 + 64 * q0)) & 511; }
 
 // ---- integer side of one blind-rotation step (trgsw.zig:270-273, 312-321, 442-466, 193-219) ----
-// coefficient e of (X^atil * acc - acc), atil in [0, 2N]
-TFHE_HD uint32_t rot_diff(const uint32_t *acc, int e, int atil) {
-    const int u = (e - atil) & (2 * kN - 1);
-    const uint32_t v = acc[u & (kN - 1)];
-    return ((u & kN) ? (0u - v) : v) - acc[e];
-}
-// role A: the 16 coefficients this thread feeds into pass 1 (re: e, im: e+512), offset pre-added
+// role A: d[2p], d[2p+1] = coefficients e and e+512 of (X^atil * acc - acc) + offset, e = 64 p + 8 k1 + k0,
+// atil in [0, 2N].  X^atil * acc at index j is acc[u] for u = (j - atil) mod 2N < N, else -acc[u - N].
+// acc is stored in acc_pos order; stepping e by 64 leaves the low 6 position bits unchanged.
 TFHE_HD void load_rot_diffs(uint32_t (&d)[16], const uint32_t *acc, int atil, uint32_t offset, int k0, int k1) {
+    const int t = 8 * k0 + k1;
+    const int u0 = (8 * k1 + k0 - atil) & (2 * kN - 1);
+    const int low6 = acc_pos(u0) & 63;
 #pragma unroll
-    for (int p = 0; p < 8; p++) {
-        const int e = 64 * p + 8 * k1 + k0;
-        d[2 * p] = rot_diff(acc, e, atil) + offset;
-        d[2 * p + 1] = rot_diff(acc, e + kHalfN, atil) + offset;
+    for (int pp = 0; pp < 16; pp++) {          // pp = p (re part) for pp < 8, p + 8 (im part, e + 512) else
+        const int u = (u0 + 64 * pp) & (2 * kN - 1);
+        const uint32_t v = acc[(u & 0x3C0) | low6];
+        const uint32_t rot = (u & kN) ? (0u - v) : v;
+        const uint32_t own = acc[64 * pp + t];
+        d[(pp & 7) * 2 + (pp >> 3)] = rot - own + offset;
     }
 }
 // gadget digit of level l (shift sh = 32 - (l+1)*bgbit) as signed integer -> double
