@@ -34,7 +34,7 @@ namespace tfhe_b200 {
 
 namespace {
 
-constexpr int kStages = 3;  // depth of the key ring (16 KiB per stage)
+constexpr int kMaxStages = 4;  // deepest key ring (16 KiB per stage); Layout<KCT>::kStages picks the depth
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bar_sync(int id, int nthreads) {
@@ -79,20 +79,21 @@ struct Producer {
     cplx *ring;
     uint64_t *full_bar, *empty_bar;
     int remaining;        // chunks still to issue
-    int issued;           // chunks issued so far (first kStages need no empty wait)
+    int issued;           // chunks issued so far (the first `stages` need no empty wait)
+    int stages;
     int stage;
     uint32_t phase;
     bool active;
 };
 __device__ __forceinline__ void producer_poll(Producer &pr) {
     if (pr.active && pr.remaining > 0) {
-        if (pr.issued < kStages || mbar_try_wait(&pr.empty_bar[pr.stage], pr.phase ^ 1)) {
+        if (pr.issued < pr.stages || mbar_try_wait(&pr.empty_bar[pr.stage], pr.phase ^ 1)) {
             mbar_arrive_expect_tx(&pr.full_bar[pr.stage], kBskChunkBytes);
             bulk_g2s(pr.ring + pr.stage * kBskChunkCplx, pr.src, kBskChunkBytes, &pr.full_bar[pr.stage]);
             pr.src += kBskChunkCplx;
             pr.remaining--;
             pr.issued++;
-            if (++pr.stage == kStages) { pr.stage = 0; pr.phase ^= 1; }
+            if (++pr.stage == pr.stages) { pr.stage = 0; pr.phase ^= 1; }
         }
     }
 }
@@ -129,10 +130,24 @@ struct Xbuf {
     int flip;     // 0 or kX2Slots
 };
 
+// Pass-2 twiddles of one thread.  FULL: r^1..r^7 resident (28 registers, KCT <= 4);
+// POW: r, r^2, r^4 resident and the rest expanded per pass (12 registers, KCT = 5, 6).
+template <bool POW>
+struct Tw2 {
+    cplx w[POW ? 3 : 7];
+    __device__ __forceinline__ void get(cplx (&out)[7]) const {
+        if (POW) expand_powers(out, w[0], w[1], w[2]);
+        else {
+#pragma unroll
+            for (int p = 0; p < 7; p++) out[p] = w[p];
+        }
+    }
+};
+
 // forward transform, role A registers in -> role C (leaf order) out
-template <bool USE_TMA, bool DBX2>
-__device__ __forceinline__ void fwd_transform(cplx (&v)[8], Xbuf &xb, const cplx *tw2, int tw2_stride, const cplx *tw3,
-                                              int tw3_stride, int hi, int lo, int barid, Producer &pr) {
+template <bool USE_TMA, bool DBX2, bool POW>
+__device__ __forceinline__ void fwd_transform(cplx (&v)[8], Xbuf &xb, const Tw2<POW> &tw2, const cplx (&tw3)[7], int hi, int lo,
+                                              int barid, Producer &pr) {
     fwd_pass1(v);
     cplx *x1 = xb.x1;
 #pragma unroll
@@ -140,7 +155,11 @@ __device__ __forceinline__ void fwd_transform(cplx (&v)[8], Xbuf &xb, const cplx
     __syncwarp();
 #pragma unroll
     for (int q = 0; q < 8; q++) v[q] = x1[x1_slot(hi, lo, q)];
-    fwd_pass(v, tw2, tw2_stride);
+    {
+        cplx w[7];
+        tw2.get(w);
+        fwd_pass(v, w, 1);
+    }
     if (USE_TMA) producer_poll(pr);
     cplx *x2 = xb.x2 + (DBX2 ? xb.flip : 0);
     if (DBX2) xb.flip ^= kX2Slots;
@@ -150,14 +169,14 @@ __device__ __forceinline__ void fwd_transform(cplx (&v)[8], Xbuf &xb, const cplx
     bar_sync(barid, kGroupThreads);
 #pragma unroll
     for (int q = 0; q < 8; q++) v[q] = x2[x2_slot(hi, lo, q)];
-    fwd_pass(v, tw3, tw3_stride);
+    fwd_pass(v, tw3, 1);
 }
 
 // inverse transform, role C (leaf order) in -> role A out: v[p] = c_e, e = 64 p + 8 lo + hi
-template <bool USE_TMA, bool DBX2>
-__device__ __forceinline__ void inv_transform(cplx (&v)[8], Xbuf &xb, const cplx *tw2, int tw2_stride, const cplx *tw3,
-                                              int tw3_stride, int hi, int lo, int barid, Producer &pr) {
-    inv_pass(v, tw3, tw3_stride);
+template <bool USE_TMA, bool DBX2, bool POW>
+__device__ __forceinline__ void inv_transform(cplx (&v)[8], Xbuf &xb, const Tw2<POW> &tw2, const cplx (&tw3)[7], int hi, int lo,
+                                              int barid, Producer &pr) {
+    inv_pass(v, tw3, 1);
     if (USE_TMA) producer_poll(pr);
     cplx *x2 = xb.x2 + (DBX2 ? xb.flip : 0);
     if (DBX2) xb.flip ^= kX2Slots;
@@ -167,7 +186,11 @@ __device__ __forceinline__ void inv_transform(cplx (&v)[8], Xbuf &xb, const cplx
     bar_sync(barid, kGroupThreads);
 #pragma unroll
     for (int q = 0; q < 8; q++) v[q] = x2[x2_slot(lo, q, hi)];
-    inv_pass(v, tw2, tw2_stride);
+    {
+        cplx w[7];
+        tw2.get(w);
+        inv_pass(v, w, 1);
+    }
     cplx *x1 = xb.x1;
 #pragma unroll
     for (int q = 0; q < 8; q++) x1[x1_slot(hi, lo, q)] = v[q];
@@ -198,32 +221,29 @@ __host__ __device__ constexpr int align16(int x) { return (x + 15) & ~15; }
 // shared-memory footprint of one ciphertext group
 template <int KCT>
 struct Layout {
-    static constexpr bool kTwRegs = KCT <= 4;   // pass-2 twiddles in registers (252-register budget)
-    static constexpr bool kTw3Regs = true;      // pass-3 twiddles in registers (fits the 168-register budget too)
+    static constexpr bool kTw2Pow = KCT > 4;    // 168-register budget: keep r, r^2, r^4 of pass 2 and expand per pass
     static constexpr bool kDbX2 = KCT <= 4;     // double-buffered X2 (fits when only 4 groups share the SM)
+    static constexpr int kStages = 3;   // key-ring depth (4 measured no faster)
     static constexpr int kAccBytes = 2 * kN * 4;
     static constexpr int kX1Bytes = kX1Slots * 16;
     static constexpr int kX2Bytes = kX2Slots * 16;
     __host__ __device__ static constexpr int group_bytes(int n) {
         return kAccBytes + kX1Bytes + (kDbX2 ? 2 : 1) * kX2Bytes + align16((n + 1) * 2);
     }
-    __host__ __device__ static constexpr int table_bytes() { return (kTw3Regs ? 0 : kTw3Len * 16) + (kTwRegs ? 0 : kTw2Len * 16); }
 };
 
 template <int KCT, bool USE_TMA, bool MARGIN>
 __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(const BrArgs P) {
     using Lay = Layout<KCT>;
-    constexpr bool TWREG = Lay::kTwRegs, TW3REG = Lay::kTw3Regs, DBX2 = Lay::kDbX2;
+    constexpr bool POW = Lay::kTw2Pow, DBX2 = Lay::kDbX2;
+    constexpr int kStages = Lay::kStages;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // ---- carve shared memory
     unsigned char *ptr = smem_raw;
     cplx *bsk_ring = reinterpret_cast<cplx *>(ptr);
     if (USE_TMA) ptr += kStages * kBskChunkBytes;
-    cplx *tw3s = reinterpret_cast<cplx *>(ptr);
-    cplx *tw2s = tw3s + (TW3REG ? 0 : kTw3Len);
-    ptr += Lay::table_bytes();
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(ptr);
-    uint64_t *empty_bar = full_bar + kStages;
+    uint64_t *empty_bar = full_bar + kMaxStages;
     ptr += 64;
     const int n = P.n, L = P.L, bgbit = P.bgbit;
     const int group_bytes = Lay::group_bytes(n);
@@ -232,10 +252,6 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
     const int first_ct = blockIdx.x * KCT;
     const int n_active = min(KCT, (int)P.B - first_ct);
 
-    if (!TW3REG)
-        for (int i = tid; i < kTw3Len; i += blockDim.x) tw3s[i] = P.tw3[i];
-    if (!TWREG)
-        for (int i = tid; i < kTw2Len; i += blockDim.x) tw2s[i] = P.tw2[i];
     if (USE_TMA && tid == 0) {
         for (int s = 0; s < kStages; s++) {
             mbar_init(&full_bar[s], 1);
@@ -260,16 +276,17 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
     uint16_t *atil = reinterpret_cast<uint16_t *>(gb + Lay::kAccBytes + Lay::kX1Bytes + (DBX2 ? 2 : 1) * Lay::kX2Bytes);
     const size_t ct = (size_t)first_ct + g;
 
-    // per-thread twiddles: role B node q2 = lo, role C node t (register-resident when TWREG)
-    cplx tw2r[7], tw3r[7];
+    // per-thread twiddles, register-resident for the whole kernel: role B node q2 = lo, role C node t
+    Tw2<POW> tw2;
+    cplx tw3[7];
 #pragma unroll
-    for (int p = 1; p < 8; p++) {
-        if (TWREG) tw2r[p - 1] = P.tw2[tw2_index(p, lo)];
-        if (TW3REG) tw3r[p - 1] = P.tw3[tw3_index(p, t)];
+    for (int p = 1; p < 8; p++) tw3[p - 1] = P.tw3[tw3_index(p, t)];
+    if (POW) {
+        tw2.w[0] = P.tw2[tw2_index(1, lo)]; tw2.w[1] = P.tw2[tw2_index(2, lo)]; tw2.w[2] = P.tw2[tw2_index(4, lo)];
+    } else {
+#pragma unroll
+        for (int p = 1; p < 8; p++) tw2.w[p - 1] = P.tw2[tw2_index(p, lo)];
     }
-    const cplx *tw2 = TWREG ? tw2r : tw2s + lo;
-    const cplx *tw3 = TW3REG ? tw3r : tw3s + t;
-    constexpr int tw2_stride = TWREG ? 1 : 8, tw3_stride = TW3REG ? 1 : 64;
 
     // ---- prologue: gate linear part (gates.zig:48-121) + modulus switch (trgsw.zig:297,312)
     {
@@ -306,9 +323,12 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
     double margin = 0.0;
     Producer pr;
     pr.src = P.bsk; pr.ring = bsk_ring; pr.full_bar = full_bar; pr.empty_bar = empty_bar;
-    pr.remaining = USE_TMA ? n * 2 * L : 0; pr.issued = 0; pr.stage = 0; pr.phase = 0;
+    pr.remaining = USE_TMA ? n * 2 * L : 0; pr.issued = 0; pr.stage = 0; pr.phase = 0; pr.stages = kStages;
     pr.active = USE_TMA && tid == 0;
-    if (USE_TMA) { producer_poll(pr); producer_poll(pr); producer_poll(pr); }   // fill the ring
+    if (USE_TMA) {   // fill the ring
+#pragma unroll
+        for (int s = 0; s < kStages; s++) producer_poll(pr);
+    }
 
     // ---- n CMUX steps (trgsw.zig:311-330)
     for (int i = 0; i < n; i++) {
@@ -326,7 +346,7 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
             for (int l = 0; l < L; l++) {
                 cplx v[8];
                 digits_to_cplx(v, d, 32 - (l + 1) * bgbit, mask, half_bg);
-                fwd_transform<USE_TMA, DBX2>(v, xb, tw2, tw2_stride, tw3, tw3_stride, hi, lo, barid, pr);
+                fwd_transform<USE_TMA, DBX2, POW>(v, xb, tw2, tw3, hi, lo, barid, pr);
                 const cplx *chunk;
                 if (USE_TMA) {
                     while (!mbar_try_wait(&full_bar[stage], phase)) producer_poll(pr);
@@ -346,9 +366,9 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
                 }
             }
         }
-        inv_transform<USE_TMA, DBX2>(oa, xb, tw2, tw2_stride, tw3, tw3_stride, hi, lo, barid, pr);
+        inv_transform<USE_TMA, DBX2, POW>(oa, xb, tw2, tw3, hi, lo, barid, pr);
         round_accumulate<MARGIN>(oa, acc_a, t, wide, margin);
-        inv_transform<USE_TMA, DBX2>(ob, xb, tw2, tw2_stride, tw3, tw3_stride, hi, lo, barid, pr);
+        inv_transform<USE_TMA, DBX2, POW>(ob, xb, tw2, tw3, hi, lo, barid, pr);
         round_accumulate<MARGIN>(ob, acc_b, t, wide, margin);
         bar_sync(barid, kGroupThreads);   // accumulator complete before the next rotated reads
     }
@@ -374,7 +394,7 @@ template <int KCT, bool USE_TMA, bool MARGIN>
 cudaError_t launch_variant(const BrArgs &a, cudaStream_t s) {
     using Lay = Layout<KCT>;
     const int threads = KCT * kGroupThreads;
-    const size_t smem = (USE_TMA ? kStages * kBskChunkBytes : 0) + Lay::table_bytes() + 64 + (size_t)KCT * Lay::group_bytes(a.n);
+    const size_t smem = (USE_TMA ? Lay::kStages * kBskChunkBytes : 0) + 64 + (size_t)KCT * Lay::group_bytes(a.n);
     auto kern = blind_rotate_kernel<KCT, USE_TMA, MARGIN>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -45,6 +45,7 @@ struct KsArgs {
     int n, basebit, iks_t, pitch;   // pitch = row length in u32 (multiple of 4)
 };
 cudaError_t launch_keyswitch(const KsArgs &a, int sm_count, cudaStream_t s, uint64_t *launches);
+extern int g_ks_tile_override;
 
 // one-time key re-layout kernels
 cudaError_t launch_permute_bsk(const double *ref_bsk, cplx *out, int n, int L, cudaStream_t s, uint64_t *launches);

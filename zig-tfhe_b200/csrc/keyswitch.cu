@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(320) keyswitch_kernel(const KsArgs P, int i_pe
 #pragma unroll
         for (int c = 0; c < CT; c++) ab[c] = abar[c * i_per_split + (i - i0)];
         const uint4 *rowp = ksk4 + ((size_t)i * t) * rows_per_pair * pitch4 + col;
+#pragma unroll 3
         for (int j = 0; j < t; j++, rowp += (size_t)rows_per_pair * pitch4) {
             const int sh = 32 - (j + 1) * basebit;
             if (BASEBIT == 2) {
@@ -149,11 +150,16 @@ __global__ void extract2_kernel(const uint32_t *lv1, uint32_t *out, uint32_t B, 
 
 }  // namespace
 
+int g_ks_tile_override = 0;   // tuning knob (tests/bench): ciphertexts per CTA, 0 = automatic
+
 cudaError_t launch_keyswitch(const KsArgs &a, int sm_count, cudaStream_t s, uint64_t *launches) {
     if (a.B == 0) return cudaSuccess;
     if (a.pitch > 320 * 4) return cudaErrorInvalidValue;
     // pick the tile so the grid fills the machine; split the i range for small batches
-    int ct = (a.B >= (uint32_t)(16 * sm_count)) ? 16 : (a.B >= (uint32_t)(8 * sm_count)) ? 8 : 4;
+    // measured on B200 at B = 65,536 (tools/ks_bench.py): tile 8 = 61 ms, 16 = 84 ms, 4 = 68 ms, 32 = 178 ms:
+    // the kernel is latency-bound, small tiles keep ~7 CTAs per SM resident and the rows hit in L1
+    int ct = (a.B >= (uint32_t)(8 * sm_count)) ? 8 : 4;
+    if (g_ks_tile_override == 4 || g_ks_tile_override == 8 || g_ks_tile_override == 16) ct = g_ks_tile_override;
     const int tiles = (a.B + ct - 1) / ct;
     int splits = 1;
     while (tiles * splits < 2 * sm_count && splits < 32) splits *= 2;

@@ -165,6 +165,12 @@ TFHE_HD void fwd_pass(cplx (&v)[8], const cplx *tw, int stride) {
     for (int p = 1; p < 8; p++) v[p] = cmul(v[p], tw[(p - 1) * stride]);
     dft8<+1>(v);
 }
+// r^1..r^7 from r, r^2, r^4 (4 complex multiplies): trades 16 FP64 operations per pass for 8 registers
+// (or 4 shared-memory loads); one extra rounding per derived power, far inside the exactness margin.
+TFHE_HD void expand_powers(cplx (&w)[7], cplx r1, cplx r2, cplx r4) {
+    w[0] = r1; w[1] = r2; w[2] = cmul(r1, r2); w[3] = r4;
+    w[4] = cmul(r1, r4); w[5] = cmul(r2, r4); w[6] = cmul(w[2], r4);
+}
 // ---- inverse passes (DFT8 with - kernel, then conjugate twiddle) ----
 TFHE_HD void inv_pass(cplx (&v)[8], const cplx *tw, int stride) {
     dft8<-1>(v);
