@@ -31,7 +31,8 @@ struct Device {
     cplx *bsk = nullptr;
     uint32_t *ksk = nullptr;
     cplx *tw2 = nullptr, *tw3 = nullptr;
-    double *exact_tables = nullptr;
+    double *exact_tables = nullptr;   // make_exact_tables(), exact mode
+    double *bsk_ref = nullptr;        // bootstrapping key in the reference layout (exact mode reads it as is)
     unsigned long long *margin_bits = nullptr;
     Buf a, b, out, lv1, ops, tv, trlwe;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // K1 start, K1 end / K2 start, K2 end (timing mode)
@@ -112,8 +113,7 @@ int run_device(tfhe_b200_ctx *c, Device &d, int op, const int32_t *d_ops, const 
     d.ev_valid = false;
     if (c->timing) CU(c, cudaEventRecord(d.ev[0], d.stream));
     if (c->mode == TFHE_B200_MODE_EXACT) {
-        if (!d.exact_tables) return fail(c, TFHE_B200_ERR_NOT_IMPLEMENTED, "exact mode tables missing");
-        CU(c, launch_blind_rotate_exact(A, d.exact_tables, d.stream, &c->launches));
+        CU(c, launch_blind_rotate_exact(A, d.exact_tables, d.bsk_ref, c->track_margin, d.stream, &c->launches));
     } else {
         CU(c, launch_blind_rotate(A, c->tune, c->track_margin, d.stream, &c->launches));
     }
@@ -217,8 +217,13 @@ int upload_key_device(tfhe_b200_ctx *c, Device &d, const double *src_bsk, bool b
     if (d.bsk) CU(c, cudaFree(d.bsk));
     CU(c, cudaMalloc(&d.bsk, bsk_doubles * 8));
     CU(c, launch_permute_bsk(d_ref, d.bsk, p.n, p.L, d.stream, &c->launches));
+    if (!staging) {   // caller's device buffer: keep our own copy of the reference layout for exact mode
+        CU(c, cudaMalloc(&staging, bsk_doubles * 8));
+        CU(c, cudaMemcpyAsync(staging, src_bsk, bsk_doubles * 8, cudaMemcpyDeviceToDevice, d.stream));
+    }
     CU(c, cudaStreamSynchronize(d.stream));
-    if (staging) CU(c, cudaFree(staging));
+    if (d.bsk_ref) CU(c, cudaFree(d.bsk_ref));
+    d.bsk_ref = staging;
 
     if (d.ksk) { CU(c, cudaFree(d.ksk)); d.ksk = nullptr; }
     if (src_ksk) {
@@ -259,6 +264,8 @@ int tfhe_b200_create(const tfhe_b200_params *params, const int *device_ids, int 
     c->ksk_pitch = ((p.n + 1) + 3) & ~3;
     cplx tw2[kTw2Len], tw3[kTw3Len];
     make_twiddle_tables(tw2, tw3);
+    std::vector<double> xt(6 * 512);
+    make_exact_tables(xt.data());
     for (int k = 0; k < n_dev; k++) {
         Device d;
         d.id = device_ids ? device_ids[k] : k;
@@ -274,6 +281,8 @@ int tfhe_b200_create(const tfhe_b200_params *params, const int *device_ids, int 
                   cudaEventCreate(&d.ev[1]) == cudaSuccess && cudaEventCreate(&d.ev[2]) == cudaSuccess &&
                   cudaMemcpy(d.tw2, tw2, sizeof(tw2), cudaMemcpyHostToDevice) == cudaSuccess &&
                   cudaMemcpy(d.tw3, tw3, sizeof(tw3), cudaMemcpyHostToDevice) == cudaSuccess &&
+                  cudaMalloc(&d.exact_tables, xt.size() * 8) == cudaSuccess &&
+                  cudaMemcpy(d.exact_tables, xt.data(), xt.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
                   cudaMemset(d.margin_bits, 0, 8) == cudaSuccess;
         c->devs.push_back(d);
         if (!ok) {
@@ -290,7 +299,7 @@ void tfhe_b200_destroy(tfhe_b200_ctx *c) {
     for (Device &d : c->devs) {
         cudaSetDevice(d.id);
         if (d.stream) cudaStreamSynchronize(d.stream);
-        for (void *p : {(void *)d.bsk, (void *)d.ksk, (void *)d.tw2, (void *)d.tw3, (void *)d.exact_tables, (void *)d.margin_bits, d.a.p, d.b.p,
+        for (void *p : {(void *)d.bsk, (void *)d.ksk, (void *)d.tw2, (void *)d.tw3, (void *)d.exact_tables, (void *)d.bsk_ref, (void *)d.margin_bits, d.a.p, d.b.p,
                         d.out.p, d.lv1.p, d.ops.p, d.tv.p, d.trlwe.p})
             if (p) cudaFree(p);
         for (cudaEvent_t e : d.ev) if (e) cudaEventDestroy(e);
@@ -497,4 +506,3 @@ double tfhe_b200_measure_fp64_tflops(tfhe_b200_ctx *c, int dev) {
 
 }  // extern "C"
 
-// exact mode is provided by blind_rotate_exact.cu

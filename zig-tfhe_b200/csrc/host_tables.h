@@ -38,4 +38,34 @@ inline void make_twiddle_tables(cplx *tw2, cplx *tw3) {
     }
 }
 
+// Exact-mode tables: the very values the reference's plan and radix-2 loop use (src/fft.zig:98-106 twists,
+// :589-611 stage twiddles from the serial recurrence w <- w * w_len), 6 x 512 doubles:
+//   [0] twist_re  [1] twist_im  [2] fwd_re  [3] fwd_im  [4] inv_re  [5] inv_im ; stage s at [2^s - 1, 2^(s+1) - 1).
+// Compiled with -ffp-contract=off so the recurrence is evaluated with separate multiplies and adds.
+inline void make_exact_tables(double *out) {
+    const double pi = 3.14159265358979323846;
+    const double twist_unit = pi / 1024.0;                         // fft.zig:101
+    for (int i = 0; i < 512; i++) {
+        const double angle = (double)i * twist_unit;               // fft.zig:103
+        out[i] = std::cos(angle);
+        out[512 + i] = std::sin(angle);
+    }
+    for (int inv = 0; inv < 2; inv++) {
+        double *tr = out + (2 + 2 * inv) * 512, *ti = tr + 512;
+        tr[511] = ti[511] = 0.0;
+        for (int len = 2; len <= 512; len *= 2) {
+            const double angle = inv ? 2.0 * pi / (double)len : -2.0 * pi / (double)len;   // fft.zig:591
+            const double wl_re = std::cos(angle), wl_im = std::sin(angle);                   // fft.zig:592-593
+            double w_re = 1.0, w_im = 0.0;
+            for (int j = 0; j < len / 2; j++) {
+                tr[len / 2 - 1 + j] = w_re;
+                ti[len / 2 - 1 + j] = w_im;
+                const double temp = w_re * wl_re - w_im * wl_im;                             // fft.zig:609
+                w_im = w_re * wl_im + w_im * wl_re;                                          // fft.zig:610
+                w_re = temp;
+            }
+        }
+    }
+}
+
 }  // namespace tfhe_b200

@@ -34,7 +34,8 @@ struct BrTuning {
 
 // returns cudaSuccess or the launch error; *launches += kernels launched
 cudaError_t launch_blind_rotate(const BrArgs &a, const BrTuning &tune, bool track_margin, cudaStream_t s, uint64_t *launches);
-cudaError_t launch_blind_rotate_exact(const BrArgs &a, const double *exact_tables, cudaStream_t s, uint64_t *launches);
+cudaError_t launch_blind_rotate_exact(const BrArgs &a, const double *exact_tables, const double *bsk_ref, bool track_margin,
+                                      cudaStream_t s, uint64_t *launches);
 
 // K2: identity key switching, lv1 [B][N+1] -> lv0 [B][n+1].  ksk_dev: [N][t][base-1][pitch] u32.
 struct KsArgs {
