@@ -1,0 +1,145 @@
+// tfhe_b200.hpp -- C++ mirror of the reference's operator interface for the gate-bootstrapping path,
+// over the C ABI of include/tfhe_b200.h.  (The reference's host language, Zig, has no toolchain in the
+// build image; this header is the compiled-language host side, and zig/cuda.zig + zig/gpu.zig are the Zig one.)
+//
+//   reference                                                  here
+//   gates.Gates{bootstrap}            src/gates.zig:25-151      tfhe_b200::Gates
+//   gates.batchNand ... batchXnor     src/gates.zig:244-295     tfhe_b200::batchNand ... batchXnor
+//   VanillaBootstrap                  src/bootstrap/vanilla.zig tfhe_b200::GpuBootstrap
+//   key.CloudKey                      src/key.zig:61-65         tfhe_b200::CloudKey (views, not owners)
+//   errors: Zig error unions                                    tfhe_b200::Error (std::runtime_error + status code)
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/tfhe_b200.h"
+
+namespace tfhe_b200 {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string &m) : std::runtime_error("tfhe_b200: " + m), code(c) {}
+};
+struct NotImplemented : Error { using Error::Error; };   // Zig: error.NotImplemented
+
+// utils.Ciphertext = tlwe.TLWELv0 (src/utils.zig:25, src/tlwe.zig:11-13): n+1 torus words, body last
+using Ciphertext = std::vector<uint32_t>;
+
+// params.SecurityParams (src/params.zig:36-67)
+inline tfhe_b200_params security_128_bit() { return {700, 1024, 3, 6, 2, 9}; }   // params.zig:350-375
+inline tfhe_b200_params security_110_bit() { return {630, 1024, 3, 6, 2, 8}; }   // params.zig:98-123
+inline tfhe_b200_params security_80_bit() { return {550, 1024, 3, 6, 2, 7}; }    // params.zig:70-95
+
+// key.CloudKey (src/key.zig:61-65) as non-owning views in the reference's layouts
+struct CloudKey {
+    uint32_t decomposition_offset;
+    const double *bootstrapping_key;        // [n][2L][2][N]
+    const uint32_t *key_switching_key;      // [N*t*base][n+1] or nullptr (CloudKey.newNoKsk, key.zig:80-100)
+};
+
+class GpuBootstrap {
+public:
+    GpuBootstrap(const tfhe_b200_params &p, const CloudKey &ck, const std::vector<int> &devices = {0}) : words_(p.n + 1) {
+        int rc = tfhe_b200_create(&p, devices.data(), (int)devices.size(), &ctx_);
+        if (rc) throw Error(rc, "no sm_100 CUDA device / bad parameters");
+        check(tfhe_b200_load_key(ctx_, ck.bootstrapping_key, ck.key_switching_key, (size_t)words_ * 4, ck.decomposition_offset));
+    }
+    GpuBootstrap(const GpuBootstrap &) = delete;
+    GpuBootstrap &operator=(const GpuBootstrap &) = delete;
+    ~GpuBootstrap() { tfhe_b200_destroy(ctx_); }
+
+    // VanillaBootstrap.bootstrap (vanilla.zig:38-52)
+    Ciphertext bootstrap(const Ciphertext &c) const {
+        Ciphertext out(words_);
+        check(tfhe_b200_bootstrap_batch(ctx_, c.data(), out.data(), 1, nullptr, 0));
+        return out;
+    }
+    // VanillaBootstrap.bootstrapWithoutKeySwitch (vanilla.zig:58-69)
+    Ciphertext bootstrapWithoutKeySwitch(const Ciphertext &c) const {
+        Ciphertext out(words_);
+        check(tfhe_b200_bootstrap_no_keyswitch_batch(ctx_, c.data(), out.data(), 1));
+        return out;
+    }
+    const char *name() const { return "b200"; }
+    tfhe_b200_ctx *ctx() const { return ctx_; }
+    int words() const { return words_; }
+    void check(int rc) const {
+        if (rc == TFHE_B200_ERR_NOT_IMPLEMENTED) throw NotImplemented(rc, tfhe_b200_last_error(ctx_));
+        if (rc) throw Error(rc, tfhe_b200_last_error(ctx_));
+    }
+
+private:
+    tfhe_b200_ctx *ctx_ = nullptr;
+    int words_;
+};
+
+// gates.Gates (gates.zig:25-151)
+class Gates {
+public:
+    explicit Gates(const GpuBootstrap &b) : b_(b) {}
+    const char *bootstrapStrategy() const { return b_.name(); }
+    Ciphertext nandGate(const Ciphertext &a, const Ciphertext &b) const { return one(TFHE_B200_NAND, a, b); }
+    Ciphertext orGate(const Ciphertext &a, const Ciphertext &b) const { return one(TFHE_B200_OR, a, b); }
+    Ciphertext andGate(const Ciphertext &a, const Ciphertext &b) const { return one(TFHE_B200_AND, a, b); }
+    Ciphertext xorGate(const Ciphertext &a, const Ciphertext &b) const { return one(TFHE_B200_XOR, a, b); }
+    Ciphertext xnorGate(const Ciphertext &a, const Ciphertext &b) const { return one(TFHE_B200_XNOR, a, b); }
+    Ciphertext norGate(const Ciphertext &a, const Ciphertext &b) const { return one(TFHE_B200_NOR, a, b); }
+    Ciphertext andNyGate(const Ciphertext &a, const Ciphertext &b) const { return one(TFHE_B200_ANDNY, a, b); }
+    Ciphertext andYnGate(const Ciphertext &a, const Ciphertext &b) const { return one(TFHE_B200_ANDYN, a, b); }
+    Ciphertext orNyGate(const Ciphertext &a, const Ciphertext &b) const { return one(TFHE_B200_ORNY, a, b); }
+    Ciphertext orYnGate(const Ciphertext &a, const Ciphertext &b) const { return one(TFHE_B200_ORYN, a, b); }
+    // gates.zig:131-134, no bootstrap
+    Ciphertext notGate(const Ciphertext &a) const {
+        Ciphertext out(a.size());
+        for (size_t i = 0; i < a.size(); i++) out[i] = 0u - a[i];
+        return out;
+    }
+    Ciphertext copy(const Ciphertext &a) const { return a; }
+    // gates.zig:144-151 (false = 1 - 2^29, kept)
+    Ciphertext constant(bool v) const {
+        Ciphertext out(b_.words(), 0u);
+        out.back() = v ? 0x20000000u : 1u - 0x20000000u;
+        return out;
+    }
+    // gates.zig:124-129
+    Ciphertext muxNaive(const Ciphertext &a, const Ciphertext &b, const Ciphertext &c) const {
+        return orGate(andGate(a, b), andGate(notGate(a), c));
+    }
+    // batch form: a, b, out are [count][n+1] contiguous
+    void batch(int op, const uint32_t *a, const uint32_t *b, uint32_t *out, size_t count) const {
+        b_.check(tfhe_b200_gate_batch(b_.ctx(), op, a, b, out, count));
+    }
+
+private:
+    Ciphertext one(int op, const Ciphertext &a, const Ciphertext &b) const {
+        Ciphertext out(a.size());
+        batch(op, a.data(), b.data(), out.data(), 1);
+        return out;
+    }
+    const GpuBootstrap &b_;
+};
+
+// gates.batch* (gates.zig:244-295): inputs as pairs, results by value
+inline std::vector<Ciphertext> batchGate(const GpuBootstrap &bs, int op, const std::vector<std::pair<Ciphertext, Ciphertext>> &in) {
+    const size_t w = bs.words(), count = in.size();
+    std::vector<uint32_t> a(count * w), b(count * w), o(count * w);
+    for (size_t i = 0; i < count; i++) {
+        std::copy(in[i].first.begin(), in[i].first.end(), a.begin() + i * w);
+        std::copy(in[i].second.begin(), in[i].second.end(), b.begin() + i * w);
+    }
+    bs.check(tfhe_b200_gate_batch(bs.ctx(), op, a.data(), b.data(), o.data(), count));
+    std::vector<Ciphertext> out(count);
+    for (size_t i = 0; i < count; i++) out[i].assign(o.begin() + i * w, o.begin() + (i + 1) * w);
+    return out;
+}
+inline auto batchNand(const GpuBootstrap &b, const std::vector<std::pair<Ciphertext, Ciphertext>> &in) { return batchGate(b, TFHE_B200_NAND, in); }
+inline auto batchAnd(const GpuBootstrap &b, const std::vector<std::pair<Ciphertext, Ciphertext>> &in) { return batchGate(b, TFHE_B200_AND, in); }
+inline auto batchOr(const GpuBootstrap &b, const std::vector<std::pair<Ciphertext, Ciphertext>> &in) { return batchGate(b, TFHE_B200_OR, in); }
+inline auto batchXor(const GpuBootstrap &b, const std::vector<std::pair<Ciphertext, Ciphertext>> &in) { return batchGate(b, TFHE_B200_XOR, in); }
+inline auto batchNor(const GpuBootstrap &b, const std::vector<std::pair<Ciphertext, Ciphertext>> &in) { return batchGate(b, TFHE_B200_NOR, in); }
+inline auto batchXnor(const GpuBootstrap &b, const std::vector<std::pair<Ciphertext, Ciphertext>> &in) { return batchGate(b, TFHE_B200_XNOR, in); }
+
+}  // namespace tfhe_b200

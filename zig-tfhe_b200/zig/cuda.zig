@@ -1,0 +1,50 @@
+//! cuda.zig -- `extern fn` view of include/tfhe_b200.h (libtfhe_b200.so, CUDA sm_100a).
+//!
+//! Drop this file into zig-tfhe's `src/` and link the library from build.zig (see INTEGRATION.md).
+//! NOTE: written against Zig 0.15.1 but NOT compiled in the authoring environment (no Zig toolchain
+//! there); the ABI it describes is exercised through the identical ctypes binding and the C++ header.
+const std = @import("std");
+
+pub const Ctx = opaque {};
+
+/// runtime mirror of params.SecurityParams (src/params.zig:36-67); extern = C layout
+pub const Params = extern struct {
+    n: i32,
+    N: i32 = 1024,
+    L: i32,
+    bgbit: i32,
+    basebit: i32,
+    iks_t: i32,
+};
+
+pub const Status = enum(c_int) { ok = 0, invalid = 1, no_device = 2, cuda = 3, no_key = 4, not_implemented = 5, _ };
+
+pub const Gate = enum(c_int) { nand = 0, @"or" = 1, @"and" = 2, xor = 3, xnor = 4, nor = 5, andny = 6, andyn = 7, orny = 8, oryn = 9 };
+
+pub const Error = error{ InvalidArgument, NoDevice, CudaFailure, NoKey, NotImplemented };
+
+pub fn check(rc: c_int) Error!void {
+    return switch (rc) {
+        0 => {},
+        1 => Error.InvalidArgument,
+        2 => Error.NoDevice,
+        4 => Error.NoKey,
+        5 => Error.NotImplemented,
+        else => Error.CudaFailure,
+    };
+}
+
+pub extern fn tfhe_b200_create(params: *const Params, device_ids: ?[*]const c_int, n_dev: c_int, out: *?*Ctx) c_int;
+pub extern fn tfhe_b200_destroy(ctx: ?*Ctx) void;
+pub extern fn tfhe_b200_last_error(ctx: ?*const Ctx) [*:0]const u8;
+pub extern fn tfhe_b200_num_devices(ctx: ?*const Ctx) c_int;
+pub extern fn tfhe_b200_load_key(ctx: *Ctx, bsk: [*]const f64, ksk: ?[*]const u32, ksk_row_stride_bytes: usize, decomposition_offset: u32) c_int;
+pub extern fn tfhe_b200_set_mode(ctx: *Ctx, mode: c_int) c_int;
+pub extern fn tfhe_b200_gate_batch(ctx: *Ctx, op: c_int, a: [*]const u32, b: [*]const u32, out: [*]u32, count: usize) c_int;
+pub extern fn tfhe_b200_gate_batch_ops(ctx: *Ctx, ops: [*]const i32, a: [*]const u32, b: [*]const u32, out: [*]u32, count: usize) c_int;
+pub extern fn tfhe_b200_bootstrap_batch(ctx: *Ctx, in: [*]const u32, out: [*]u32, count: usize, testvec: ?[*]const u32, tv_per_item: c_int) c_int;
+pub extern fn tfhe_b200_bootstrap_no_keyswitch_batch(ctx: *Ctx, in: [*]const u32, out: [*]u32, count: usize) c_int;
+pub extern fn tfhe_b200_blind_rotate_batch(ctx: *Ctx, in: [*]const u32, trlwe_out: [*]u32, count: usize, testvec: ?[*]const u32, tv_per_item: c_int) c_int;
+pub extern fn tfhe_b200_keyswitch_batch(ctx: *Ctx, lv1: [*]const u32, lv0: [*]u32, count: usize) c_int;
+pub extern fn tfhe_b200_not_batch(ctx: *Ctx, a: [*]const u32, out: [*]u32, count: usize) c_int;
+pub extern fn tfhe_b200_sync(ctx: *Ctx) c_int;
