@@ -146,12 +146,14 @@ int run_host(tfhe_b200_ctx *c, int op, const int32_t *ops, const uint32_t *a, co
     // all devices proceed chunk-round by chunk-round; within a round work is asynchronous per device
     std::vector<size_t> lo(nd), hi(nd), pos(nd);
     for (int k = 0; k < nd; k++) { lo[k] = B * k / nd; hi[k] = B * (k + 1) / nd; pos[k] = lo[k]; }
+    std::vector<size_t> round_off(nd), round_nb(nd);
     bool more = true;
     while (more) {
         more = false;
         for (int k = 0; k < nd; k++) {
             Device &d = c->devs[k];
             const size_t nb = std::min(c->max_chunk, hi[k] - pos[k]);
+            round_nb[k] = 0;
             if (nb == 0) continue;
             const size_t off = pos[k];
             CU(c, cudaSetDevice(d.id));
@@ -190,9 +192,18 @@ int run_host(tfhe_b200_ctx *c, int op, const int32_t *ops, const uint32_t *a, co
                 if (!r) CU(c, launch_extract2((uint32_t *)d.lv1.p, d_out, (uint32_t)nb, c->prm.n, d.stream, &c->launches));
             }
             if (r) return r;
-            CU(c, cudaMemcpyAsync((uint32_t *)out + off * wout, d_out, nb * wout * 4, cudaMemcpyDeviceToHost, d.stream));
+            round_off[k] = off;
+            round_nb[k] = nb;
             pos[k] += nb;
             if (pos[k] < hi[k]) more = true;
+        }
+        // second phase: copy back.  A D2H copy into pageable memory blocks the host until that device is done, so it
+        // is issued only after EVERY device has its kernels in flight (the devices run concurrently).
+        for (int k = 0; k < nd; k++) {
+            if (round_nb[k] == 0) continue;
+            Device &d = c->devs[k];
+            CU(c, cudaSetDevice(d.id));
+            CU(c, cudaMemcpyAsync((uint32_t *)out + round_off[k] * wout, d.out.p, round_nb[k] * wout * 4, cudaMemcpyDeviceToHost, d.stream));
         }
         for (int k = 0; k < nd; k++) {
             CU(c, cudaSetDevice(c->devs[k].id));
