@@ -318,15 +318,23 @@ def main():
         kct = args.kct or 4
         waves = -(-B // (148 * kct))
         io_bytes = B * (2 * w * 4 + 4 + 4100)           # two operands + opcode in, one lv1 sample out
+        traffic = None                                  # dram bytes per launch of K1 from the committed ncu capture
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_k1_traffic.json")))
+            if B == BATCH and not args.kct:
+                traffic = tr["dram_bytes_total"]
+        except Exception:
+            pass
         roofline = {
             "kernel": "blind_rotate_kernel", "bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
-            "frac": achieved_tflops / fp64_peak if fp64_peak > 0 else None, "traffic": None,
+            "frac": achieved_tflops / fp64_peak if fp64_peak > 0 else None, "traffic": traffic,
+            "traffic_source": "profiles/r01_k1_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, one launch of this workload)",
             "peak_source": "measured live by tfhe_b200_measure_fp64_tflops (DFMA microbenchmark); MEASURED_PEAKS.json has no FP64 figure",
             "algorithmic_flop_per_bootstrap": FLOP_PER_BOOTSTRAP, "kernel_ms": k1, "kernel_share_of_step": k1 / (k1 + k2),
-            "hbm": {"algorithmic_bytes": BSK_BYTES + io_bytes, "achieved_gbs": (BSK_BYTES + io_bytes) / (k1 * 1e-3) / 1e9,
+            "hbm": {"algorithmic_bytes": BSK_BYTES * waves + io_bytes, "achieved_gbs": (BSK_BYTES * waves + io_bytes) / (k1 * 1e-3) / 1e9,
                     "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
-                    "note": "the bootstrapping key (68.8 MB) is L2-resident and read from HBM once per launch; each of the "
-                            f"{waves} CTA waves re-streams it from L2 ({BSK_BYTES * waves / 1e9:.1f} GB of L2->SM traffic per launch)"},
+                    "note": f"north_star's amortised-key term: each of the {waves} lock-step CTA waves ({148 * kct} bootstraps) streams the "
+                            "68.8 MB key from HBM once and shares it through L2; far from the HBM bound (the kernel is FP64/shared-memory bound)"},
             "keyswitch": {"kernel_ms": k2, "algorithmic_bytes": KSK_BYTES * 3 // 4 + B * (4100 + w * 4),
                           "achieved_gbs": (KSK_BYTES * 3 // 4 + B * (4100 + w * 4)) / (k2 * 1e-3) / 1e9},
         }

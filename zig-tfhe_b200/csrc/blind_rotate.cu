@@ -45,6 +45,7 @@ struct Producer {
     int remaining;        // chunks still to issue
     int issued;           // chunks issued so far (the first `stages` need no empty wait)
     int stages;
+    uint64_t policy;      // L2 evict_last for the key stream
     int stage;
     uint32_t phase;
     bool active;
@@ -53,7 +54,7 @@ __device__ __forceinline__ void producer_poll(Producer &pr) {
     if (pr.active && pr.remaining > 0) {
         if (pr.issued < pr.stages || mbar_try_wait(&pr.empty_bar[pr.stage], pr.phase ^ 1)) {
             mbar_arrive_expect_tx(&pr.full_bar[pr.stage], kBskChunkBytes);
-            bulk_g2s(pr.ring + pr.stage * kBskChunkCplx, pr.src, kBskChunkBytes, &pr.full_bar[pr.stage]);
+            bulk_g2s(pr.ring + pr.stage * kBskChunkCplx, pr.src, kBskChunkBytes, &pr.full_bar[pr.stage], pr.policy);
             pr.src += kBskChunkCplx;
             pr.remaining--;
             pr.issued++;
@@ -86,8 +87,8 @@ struct Tw2 {
 };
 
 // forward transform, role A registers in -> role C (leaf order) out
-template <bool USE_TMA, bool DBX2, bool POW>
-__device__ __forceinline__ void fwd_transform(cplx (&v)[8], Xbuf &xb, const Tw2<POW> &tw2, const cplx (&tw3)[7], int hi, int lo,
+template <bool USE_TMA, bool DBX2, bool POW, bool POW3>
+__device__ __forceinline__ void fwd_transform(cplx (&v)[8], Xbuf &xb, const Tw2<POW> &tw2, const Tw2<POW3> &tw3, int hi, int lo,
                                               int barid, Producer &pr) {
     fwd_pass1(v);
     cplx *x1 = xb.x1;
@@ -110,14 +111,22 @@ __device__ __forceinline__ void fwd_transform(cplx (&v)[8], Xbuf &xb, const Tw2<
     bar_sync(barid, kGroupThreads);
 #pragma unroll
     for (int q = 0; q < 8; q++) v[q] = x2[x2_slot(hi, lo, q)];
-    fwd_pass(v, tw3, 1);
+    {
+        cplx w[7];
+        tw3.get(w);
+        fwd_pass(v, w, 1);
+    }
 }
 
 // inverse transform, role C (leaf order) in -> role A out: v[p] = c_e, e = 64 p + 8 lo + hi
-template <bool USE_TMA, bool DBX2, bool POW>
-__device__ __forceinline__ void inv_transform(cplx (&v)[8], Xbuf &xb, const Tw2<POW> &tw2, const cplx (&tw3)[7], int hi, int lo,
+template <bool USE_TMA, bool DBX2, bool POW, bool POW3>
+__device__ __forceinline__ void inv_transform(cplx (&v)[8], Xbuf &xb, const Tw2<POW> &tw2, const Tw2<POW3> &tw3, int hi, int lo,
                                               int barid, Producer &pr) {
-    inv_pass(v, tw3, 1);
+    {
+        cplx w[7];
+        tw3.get(w);
+        inv_pass(v, w, 1);
+    }
     if (USE_TMA) producer_poll(pr);
     cplx *x2 = xb.x2 + (DBX2 ? xb.flip : 0);
     if (DBX2) xb.flip ^= kX2Slots;
@@ -139,6 +148,28 @@ __device__ __forceinline__ void inv_transform(cplx (&v)[8], Xbuf &xb, const Tw2<
 #pragma unroll
     for (int q = 0; q < 8; q++) v[q] = x1[x1_slot(hi, q, lo)];
     inv_pass1(v);
+}
+
+// 8 complex accumulators <-> 32 TMEM columns of this thread's lane
+__device__ __forceinline__ void tmem_load_cplx8(cplx (&o)[8], uint32_t taddr) {
+    uint32_t r[32];
+    tmem_wait_st();                 // our own earlier stores to these columns have landed
+    tmem_ld32(taddr, r);
+    tmem_wait_ld();
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        o[q].re = __hiloint2double((int)r[4 * q + 1], (int)r[4 * q]);
+        o[q].im = __hiloint2double((int)r[4 * q + 3], (int)r[4 * q + 2]);
+    }
+}
+__device__ __forceinline__ void tmem_store_cplx8(uint32_t taddr, const cplx (&o)[8]) {
+    uint32_t r[32];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        r[4 * q] = (uint32_t)__double2loint(o[q].re); r[4 * q + 1] = (uint32_t)__double2hiint(o[q].re);
+        r[4 * q + 2] = (uint32_t)__double2loint(o[q].im); r[4 * q + 3] = (uint32_t)__double2hiint(o[q].im);
+    }
+    tmem_st32(taddr, r);
 }
 
 template <bool MARGIN>
@@ -163,8 +194,11 @@ __host__ __device__ constexpr int align16(int x) { return (x + 15) & ~15; }
 template <int KCT>
 struct Layout {
     static constexpr bool kTw2Pow = KCT > 4;    // 168-register budget: keep r, r^2, r^4 of pass 2 and expand per pass
+    static constexpr bool kTw3Pow = KCT > 5;    // same for pass 3
     static constexpr bool kDbX2 = KCT <= 4;     // double-buffered X2 (fits when only 4 groups share the SM)
     static constexpr int kStages = 3;   // key-ring depth (4 measured no faster)
+    static constexpr bool kAccTmem = KCT > 5;   // MAC accumulators in TMEM (KCT = 6 only; measured slower than KCT = 4)
+    static constexpr int kTmemCols = 256;       // 64 columns per warp, up to 3 warps per TMEM quadrant
     static constexpr int kAccBytes = 2 * kN * 4;
     static constexpr int kX1Bytes = kX1Slots * 16;
     static constexpr int kX2Bytes = kX2Slots * 16;
@@ -176,8 +210,9 @@ struct Layout {
 template <int KCT, bool USE_TMA, bool MARGIN>
 __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(const BrArgs P) {
     using Lay = Layout<KCT>;
-    constexpr bool POW = Lay::kTw2Pow, DBX2 = Lay::kDbX2;
+    constexpr bool POW = Lay::kTw2Pow, POW3 = Lay::kTw3Pow, DBX2 = Lay::kDbX2;
     constexpr int kStages = Lay::kStages;
+    constexpr bool ACCT = Lay::kAccTmem;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // ---- carve shared memory
     unsigned char *ptr = smem_raw;
@@ -185,7 +220,8 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
     if (USE_TMA) ptr += kStages * kBskChunkBytes;
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(ptr);
     uint64_t *empty_bar = full_bar + kMaxStages;
-    ptr += 64;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(ptr + 64);
+    ptr += 80;
     const int n = P.n, L = P.L, bgbit = P.bgbit;
     const int group_bytes = Lay::group_bytes(n);
 
@@ -201,12 +237,23 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    if (ACCT && tid < 32) {
+        tmem_alloc(tmem_slot, Lay::kTmemCols);
+        tmem_fence_before_sync();
+    }
     __syncthreads();
+    uint32_t tmem_base = 0;
+    if (ACCT) {
+        tmem_fence_after_sync();
+        tmem_base = *tmem_slot;
+    }
 
     const int g = tid >> 6, t = tid & 63;
-    if (g >= n_active) return;
+    if (g >= n_active) return;   // (warp 0 belongs to group 0, always active: it frees the TMEM allocation at the end)
     const int hi = t >> 3, lo = t & 7;
     const int barid = 1 + g;
+    // this warp's TMEM window: lane quadrant (warp & 3), 64 columns per warp sharing that quadrant
+    const uint32_t my_tmem = tmem_base + ((uint32_t)((tid >> 5) & 3) << 21) + (uint32_t)(tid >> 7) * 64u;
     unsigned char *gb = ptr + (size_t)g * group_bytes;
     uint32_t *acc_a = reinterpret_cast<uint32_t *>(gb);
     uint32_t *acc_b = acc_a + kN;
@@ -219,9 +266,13 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
 
     // per-thread twiddles, register-resident for the whole kernel: role B node q2 = lo, role C node t
     Tw2<POW> tw2;
-    cplx tw3[7];
+    Tw2<POW3> tw3;
+    if (POW3) {
+        tw3.w[0] = P.tw3[tw3_index(1, t)]; tw3.w[1] = P.tw3[tw3_index(2, t)]; tw3.w[2] = P.tw3[tw3_index(4, t)];
+    } else {
 #pragma unroll
-    for (int p = 1; p < 8; p++) tw3[p - 1] = P.tw3[tw3_index(p, t)];
+        for (int p = 1; p < 8; p++) tw3.w[p - 1] = P.tw3[tw3_index(p, t)];
+    }
     if (POW) {
         tw2.w[0] = P.tw2[tw2_index(1, lo)]; tw2.w[1] = P.tw2[tw2_index(2, lo)]; tw2.w[2] = P.tw2[tw2_index(4, lo)];
     } else {
@@ -266,6 +317,7 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
     pr.src = P.bsk; pr.ring = bsk_ring; pr.full_bar = full_bar; pr.empty_bar = empty_bar;
     pr.remaining = USE_TMA ? n * 2 * L : 0; pr.issued = 0; pr.stage = 0; pr.phase = 0; pr.stages = kStages;
     pr.active = USE_TMA && tid == 0;
+    pr.policy = pr.active ? l2_policy_evict_last() : 0;
     if (USE_TMA) {   // fill the ring
 #pragma unroll
         for (int s = 0; s < kStages; s++) producer_poll(pr);
@@ -274,43 +326,92 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
     // ---- n CMUX steps (trgsw.zig:311-330)
     for (int i = 0; i < n; i++) {
         const int at = atil[i];
-        cplx oa[8], ob[8];
+        if (!ACCT) {
+            // ---- accumulators in registers (252-register budget)
+            cplx oa[8], ob[8];
 #pragma unroll
-        for (int q = 0; q < 8; q++) { oa[q] = cplx{0.0, 0.0}; ob[q] = cplx{0.0, 0.0}; }
-
+            for (int q = 0; q < 8; q++) { oa[q] = cplx{0.0, 0.0}; ob[q] = cplx{0.0, 0.0}; }
 #pragma unroll 1
-        for (int h = 0; h < 2; h++) {          // h = 0: digits of the a polynomial, 1: of b (trgsw.zig:211-217)
-            const uint32_t *accp = h ? acc_b : acc_a;
-            uint32_t d[16];
-            load_rot_diffs(d, accp, at, offset, hi, lo);
+            for (int h = 0; h < 2; h++) {          // h = 0: digits of the a polynomial, 1: of b (trgsw.zig:211-217)
+                const uint32_t *accp = h ? acc_b : acc_a;
+                uint32_t d[16];
+                load_rot_diffs(d, accp, at, offset, hi, lo);
 #pragma unroll 1
-            for (int l = 0; l < L; l++) {
-                cplx v[8];
-                digits_to_cplx(v, d, 32 - (l + 1) * bgbit, mask, half_bg);
-                fwd_transform<USE_TMA, DBX2, POW>(v, xb, tw2, tw3, hi, lo, barid, pr);
-                const cplx *chunk;
-                if (USE_TMA) {
-                    while (!mbar_try_wait(&full_bar[stage], phase)) producer_poll(pr);
-                    chunk = bsk_ring + stage * kBskChunkCplx;
-                } else {
-                    chunk = P.bsk + ((size_t)i * 2 * L + h * L + l) * kBskChunkCplx;
-                }
+                for (int l = 0; l < L; l++) {
+                    cplx v[8];
+                    digits_to_cplx(v, d, 32 - (l + 1) * bgbit, mask, half_bg);
+                    fwd_transform<USE_TMA, DBX2, POW, POW3>(v, xb, tw2, tw3, hi, lo, barid, pr);
+                    const cplx *chunk;
+                    if (USE_TMA) {
+                        while (!mbar_try_wait(&full_bar[stage], phase)) producer_poll(pr);
+                        chunk = bsk_ring + stage * kBskChunkCplx;
+                    } else {
+                        chunk = P.bsk + ((size_t)i * 2 * L + h * L + l) * kBskChunkCplx;
+                    }
 #pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    cmac(oa[q], v[q], chunk[bsk_slot(0, q, t)]);
-                    cmac(ob[q], v[q], chunk[bsk_slot(1, q, t)]);
-                }
-                if (USE_TMA) {
-                    __syncwarp();
-                    if ((t & 31) == 0) mbar_arrive(&empty_bar[stage]);
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    for (int q = 0; q < 8; q++) {
+                        cmac(oa[q], v[q], chunk[bsk_slot(0, q, t)]);
+                        cmac(ob[q], v[q], chunk[bsk_slot(1, q, t)]);
+                    }
+                    if (USE_TMA) {
+                        __syncwarp();
+                        if ((t & 31) == 0) mbar_arrive(&empty_bar[stage]);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
                 }
             }
+            inv_transform<USE_TMA, DBX2, POW, POW3>(oa, xb, tw2, tw3, hi, lo, barid, pr);
+            round_accumulate<MARGIN>(oa, acc_a, t, wide, margin);
+            inv_transform<USE_TMA, DBX2, POW, POW3>(ob, xb, tw2, tw3, hi, lo, barid, pr);
+            round_accumulate<MARGIN>(ob, acc_b, t, wide, margin);
+        } else {
+            // ---- accumulators in TMEM (168-register budget): each half is loaded, updated and stored back
+#pragma unroll 1
+            for (int h = 0; h < 2; h++) {
+                const uint32_t *accp = h ? acc_b : acc_a;
+                uint32_t d[16];
+                load_rot_diffs(d, accp, at, offset, hi, lo);
+#pragma unroll 1
+                for (int l = 0; l < L; l++) {
+                    cplx v[8];
+                    digits_to_cplx(v, d, 32 - (l + 1) * bgbit, mask, half_bg);
+                    fwd_transform<USE_TMA, DBX2, POW, POW3>(v, xb, tw2, tw3, hi, lo, barid, pr);
+                    const cplx *chunk;
+                    if (USE_TMA) {
+                        while (!mbar_try_wait(&full_bar[stage], phase)) producer_poll(pr);
+                        chunk = bsk_ring + stage * kBskChunkCplx;
+                    } else {
+                        chunk = P.bsk + ((size_t)i * 2 * L + h * L + l) * kBskChunkCplx;
+                    }
+                    const bool first = (h == 0 && l == 0);
+#pragma unroll 1
+                    for (int ab = 0; ab < 2; ab++) {
+                        cplx o[8];
+                        if (first) {
+#pragma unroll
+                            for (int q = 0; q < 8; q++) o[q] = cplx{0.0, 0.0};
+                        } else {
+                            tmem_load_cplx8(o, my_tmem + 32 * ab);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 8; q++) cmac(o[q], v[q], chunk[bsk_slot(ab, q, t)]);
+                        tmem_store_cplx8(my_tmem + 32 * ab, o);
+                    }
+                    if (USE_TMA) {
+                        __syncwarp();
+                        if ((t & 31) == 0) mbar_arrive(&empty_bar[stage]);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+#pragma unroll 1
+            for (int ab = 0; ab < 2; ab++) {
+                cplx o[8];
+                tmem_load_cplx8(o, my_tmem + 32 * ab);
+                inv_transform<USE_TMA, DBX2, POW, POW3>(o, xb, tw2, tw3, hi, lo, barid, pr);
+                round_accumulate<MARGIN>(o, ab ? acc_b : acc_a, t, wide, margin);
+            }
         }
-        inv_transform<USE_TMA, DBX2, POW>(oa, xb, tw2, tw3, hi, lo, barid, pr);
-        round_accumulate<MARGIN>(oa, acc_a, t, wide, margin);
-        inv_transform<USE_TMA, DBX2, POW>(ob, xb, tw2, tw3, hi, lo, barid, pr);
-        round_accumulate<MARGIN>(ob, acc_b, t, wide, margin);
         bar_sync(barid, kGroupThreads);   // accumulator complete before the next rotated reads
     }
 
@@ -329,13 +430,22 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
         for (int s = 16; s > 0; s >>= 1) margin = fmax(margin, __shfl_xor_sync(0xffffffffu, margin, s));
         if ((t & 31) == 0) atomicMax(P.margin_bits, (unsigned long long)__double_as_longlong(margin));
     }
+    if (ACCT) {
+        tmem_wait_st();
+        tmem_fence_before_sync();
+        bar_sync(15, n_active * kGroupThreads);      // every active warp is done with its TMEM window
+        if (tid < 32) {
+            tmem_fence_after_sync();
+            tmem_dealloc(tmem_base, Lay::kTmemCols);
+        }
+    }
 }
 
 template <int KCT, bool USE_TMA, bool MARGIN>
 cudaError_t launch_variant(const BrArgs &a, cudaStream_t s) {
     using Lay = Layout<KCT>;
     const int threads = KCT * kGroupThreads;
-    const size_t smem = (USE_TMA ? Lay::kStages * kBskChunkBytes : 0) + 64 + (size_t)KCT * Lay::group_bytes(a.n);
+    const size_t smem = (USE_TMA ? Lay::kStages * kBskChunkBytes : 0) + 80 + (size_t)KCT * Lay::group_bytes(a.n);
     auto kern = blind_rotate_kernel<KCT, USE_TMA, MARGIN>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -355,7 +465,18 @@ cudaError_t launch_kct(const BrArgs &a, bool tma, bool margin, cudaStream_t s) {
 cudaError_t launch_blind_rotate(const BrArgs &a, const BrTuning &tune, bool track_margin, cudaStream_t s, uint64_t *launches) {
     if (a.B == 0) return cudaSuccess;
     int kct = tune.kct;
-    if (kct <= 0) kct = (a.B >= 148u * 4u) ? 4 : (a.B >= 148u * 2u) ? 2 : 1;
+    if (kct <= 0) {
+        // minimise (number of CTA waves) x (time of one CTA at that width); CTA times measured on B200 at n = 700
+        // (profiles/r01_first_light*.log): 1 or 2 ciphertexts 4.5 ms, 3: 6.1 ms, 4: 6.5 ms
+        static const double t_cta[5] = {0.0, 4.5, 4.5, 6.1, 6.46};
+        const unsigned sms = tune.sm_count > 0 ? (unsigned)tune.sm_count : 148u;
+        double best = 1e30;
+        for (int k = 1; k <= 4; k++) {
+            const unsigned waves = (a.B + sms * k - 1) / (sms * k);
+            const double cost = waves * t_cta[k];
+            if (cost < best - 1e-9) { best = cost; kct = k; }
+        }
+    }
     if (launches) (*launches)++;
     switch (kct) {
         case 1: return launch_kct<1>(a, tune.use_tma != 0, track_margin, s);

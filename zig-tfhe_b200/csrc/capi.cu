@@ -115,7 +115,9 @@ int run_device(tfhe_b200_ctx *c, Device &d, int op, const int32_t *d_ops, const 
     if (c->mode == TFHE_B200_MODE_EXACT) {
         CU(c, launch_blind_rotate_exact(A, d.exact_tables, d.bsk_ref, c->track_margin, d.stream, &c->launches));
     } else {
-        CU(c, launch_blind_rotate(A, c->tune, c->track_margin, d.stream, &c->launches));
+        BrTuning tune = c->tune;
+        tune.sm_count = d.sm_count;
+        CU(c, launch_blind_rotate(A, tune, c->track_margin, d.stream, &c->launches));
     }
     if (c->timing) CU(c, cudaEventRecord(d.ev[1], d.stream));
     if (d_lv0) {

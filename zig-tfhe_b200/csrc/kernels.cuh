@@ -30,6 +30,7 @@ struct BrArgs {
 struct BrTuning {
     int kct = 0;        // ciphertexts per CTA (0 = default)
     int use_tma = 1;    // stream key chunks with cp.async.bulk + mbarrier (0: direct global loads)
+    int sm_count = 0;   // SMs of the target device (wave-quantisation aware choice of kct)
 };
 
 // returns cudaSuccess or the launch error; *launches += kernels launched
