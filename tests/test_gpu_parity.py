@@ -206,3 +206,23 @@ def test_chunked_launches_equal_single_launch(ctx128, orc128, keys128):
         assert (ctx128.gate_batch(O.AND, ca, cb) == one).all()
     finally:
         ctx128.set_tuning("max_chunk", 1 << 18)
+
+
+def test_latency_mode_equals_throughput_mode(ctx128, orc128, keys128):
+    """batches <= SM count run one CTA per ciphertext with the 2L transforms in parallel; same bits"""
+    a, b, ca, cb = _enc_pairs(orc128, keys128, 40, seed=14)
+    lat = ctx128.gate_batch(O.XOR, ca, cb)
+    ctx128.set_tuning("latency_mode", 0)
+    try:
+        thr = ctx128.gate_batch(O.XOR, ca, cb)
+    finally:
+        ctx128.set_tuning("latency_mode", 1)
+    assert (lat == thr).all()
+    assert (lat[:6] == orc128.gate_batch(O.XOR, ca[:6], cb[:6], keys128)).all()
+    ctx128.track_margin(True)
+    try:
+        ctx128.max_round_margin(reset=True)
+        ctx128.gate_batch(O.XOR, ca, cb)
+        assert 0.0 < ctx128.max_round_margin(reset=True) < 0.25
+    finally:
+        ctx128.track_margin(False)

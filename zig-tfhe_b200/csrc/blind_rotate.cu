@@ -441,6 +441,149 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Latency mode (batches no larger than the SM count): one CTA per ciphertext, the 2L digit transforms of an
+// iteration run concurrently on 2L groups of 64 threads instead of one after another.  Group r transforms
+// digit polynomial r and multiplies it with key row r (loaded straight from L2 at the top of the iteration);
+// the 2L products are reduced through shared memory by groups 0 (a part) and 1 (b part), which then run the
+// two inverse transforms.  Same building blocks and layouts as the throughput kernel; the sum over rows is
+// associated differently (separately rounded products), which rounds to the same integers wherever the
+// external product is exact (the launcher only selects this kernel for those parameter sets).
+template <int L, bool MARGIN>
+__global__ void __launch_bounds__(2 * L * kGroupThreads, 1) blind_rotate_latency_kernel(const BrArgs P) {
+    constexpr int G = 2 * L;
+    constexpr bool POW = (L >= 3);    // 384 threads -> 168 registers: expand twiddle powers per pass
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t *acc_a = reinterpret_cast<uint32_t *>(smem_raw), *acc_b = acc_a + kN;
+    cplx *red = reinterpret_cast<cplx *>(smem_raw + 2 * kN * 4);                      // [G][ab][q][t]
+    unsigned char *xbase = smem_raw + 2 * kN * 4 + (size_t)G * kBskChunkBytes;
+    constexpr int kXBytes = (kX1Slots + kX2Slots) * 16;
+    uint64_t *key_bar = reinterpret_cast<uint64_t *>(xbase + G * kXBytes);           // one mbarrier per group
+    uint16_t *atil = reinterpret_cast<uint16_t *>(xbase + G * kXBytes + 64);
+    const int n = P.n, bgbit = P.bgbit;
+    const int tid = threadIdx.x, g = tid >> 6, t = tid & 63, hi = t >> 3, lo = t & 7;
+    const int barid = 1 + g;
+    const size_t ct = blockIdx.x;
+    // Key row r of iteration i lands by cp.async.bulk directly in this group's slice of the reduction buffer
+    // (identical [ab][q][t] layout): the thread that reads a key value overwrites it with its product.
+    cplx *my_red = red + (size_t)g * kBskChunkCplx;
+    const uint64_t policy = l2_policy_evict_last();
+    if (t == 0) {
+        mbar_init(&key_bar[g], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive_expect_tx(&key_bar[g], kBskChunkBytes);
+        bulk_g2s(my_red, P.bsk + (size_t)g * kBskChunkCplx, kBskChunkBytes, &key_bar[g], policy);
+    }
+    Xbuf xb;
+    xb.x1 = reinterpret_cast<cplx *>(xbase + g * kXBytes);
+    xb.x2 = xb.x1 + kX1Slots;
+    xb.flip = 0;
+    Tw2<POW> tw2;
+    Tw2<POW> tw3;
+    if (POW) {
+        tw2.w[0] = P.tw2[tw2_index(1, lo)]; tw2.w[1] = P.tw2[tw2_index(2, lo)]; tw2.w[2] = P.tw2[tw2_index(4, lo)];
+        tw3.w[0] = P.tw3[tw3_index(1, t)]; tw3.w[1] = P.tw3[tw3_index(2, t)]; tw3.w[2] = P.tw3[tw3_index(4, t)];
+    } else {
+#pragma unroll
+        for (int p = 1; p < 8; p++) { tw2.w[p - 1] = P.tw2[tw2_index(p, lo)]; tw3.w[p - 1] = P.tw3[tw3_index(p, t)]; }
+    }
+    {   // prologue: gate linear part + modulus switch, whole CTA
+        const int op = P.ops ? P.ops[ct] : P.op;
+        const uint32_t *ia = P.in_a + ct * (size_t)(n + 1);
+        const uint32_t *ib = (op >= 0) ? P.in_b + ct * (size_t)(n + 1) : ia;
+        for (int i = tid; i <= n; i += G * kGroupThreads) {
+            uint32_t lin = gate_linear(op, ia[i], ib[i]);
+            if (i == n) lin += gate_constant(op);
+            const uint32_t m = (uint32_t)(((unsigned long long)lin + (1u << 20)) >> 21);
+            atil[i] = (uint16_t)((i == n) ? (2 * kN - m) : m);
+        }
+    }
+    __syncthreads();
+    {
+        const int btil = atil[n];
+        const uint32_t *tv = P.testvec ? P.testvec + (P.tv_per_item ? ct * (size_t)(2 * kN) : 0) : nullptr;
+        for (int j = tid; j < kN; j += G * kGroupThreads) {
+            const int u = (j - btil) & (2 * kN - 1);
+            const uint32_t va = tv ? tv[u & (kN - 1)] : 0u;
+            const uint32_t vb = tv ? tv[kN + (u & (kN - 1))] : 0x20000000u;
+            acc_a[acc_pos(j)] = (u & kN) ? 0u - va : va;
+            acc_b[acc_pos(j)] = (u & kN) ? 0u - vb : vb;
+        }
+    }
+    __syncthreads();
+
+    const uint32_t mask = (1u << bgbit) - 1u, half_bg = 1u << (bgbit - 1);
+    const int wide = P.wide_round;
+    const int h = g / L, l = g - h * L;
+    const int sh = 32 - (l + 1) * bgbit;
+    double margin = 0.0;
+    Producer pr;
+    pr.active = false; pr.remaining = 0;
+    for (int i = 0; i < n; i++) {
+        const int at = atil[i];
+        cplx v[8];
+        {
+            uint32_t d[16];
+            load_rot_diffs(d, h ? acc_b : acc_a, at, P.offset, hi, lo);
+            digits_to_cplx(v, d, sh, mask, half_bg);
+        }
+        fwd_transform<false, false, POW, POW>(v, xb, tw2, tw3, hi, lo, barid, pr);
+        mbar_wait(&key_bar[g], (uint32_t)(i & 1));
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            my_red[bsk_slot(0, q, t)] = cmul(v[q], my_red[bsk_slot(0, q, t)]);
+            my_red[bsk_slot(1, q, t)] = cmul(v[q], my_red[bsk_slot(1, q, t)]);
+        }
+        __syncthreads();
+        if (g < 2) {   // group 0 reduces and inverts the a part, group 1 the b part
+            cplx o[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) o[q] = red[g * 512 + q * 64 + t];
+#pragma unroll
+            for (int r = 1; r < G; r++) {
+#pragma unroll
+                for (int q = 0; q < 8; q++) o[q] = cadd(o[q], red[(r * 2 + g) * 512 + q * 64 + t]);
+            }
+            // all 2L products are consumed (both reducers read every group's slice): the barrier below orders those
+            // generic-proxy reads before the async-proxy refill issued after it
+            inv_transform<false, false, POW, POW>(o, xb, tw2, tw3, hi, lo, barid, pr);
+            round_accumulate<MARGIN>(o, g ? acc_b : acc_a, t, wide, margin);
+        }
+        __syncthreads();
+        if (t == 0 && i + 1 < n) {   // prefetch the next iteration's key row; its latency hides behind the forward transform
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive_expect_tx(&key_bar[g], kBskChunkBytes);
+            bulk_g2s(my_red, P.bsk + ((size_t)(i + 1) * G + g) * kBskChunkCplx, kBskChunkBytes, &key_bar[g], policy);
+        }
+    }
+    if (P.out_trlwe) {
+        uint32_t *o = P.out_trlwe + ct * (size_t)(2 * kN);
+        for (int j = tid; j < kN; j += G * kGroupThreads) { o[j] = acc_a[acc_pos(j)]; o[kN + j] = acc_b[acc_pos(j)]; }
+    }
+    if (P.out_lv1) {
+        uint32_t *o = P.out_lv1 + ct * (size_t)(kN + 1);
+        for (int j = tid; j <= kN; j += G * kGroupThreads)
+            o[j] = (j == 0) ? acc_a[0] : (j == kN) ? acc_b[0] : 0u - acc_a[acc_pos(kN - j)];
+    }
+    if (MARGIN && P.margin_bits) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) margin = fmax(margin, __shfl_xor_sync(0xffffffffu, margin, s));
+        if ((t & 31) == 0) atomicMax(P.margin_bits, (unsigned long long)__double_as_longlong(margin));
+    }
+}
+
+template <int L, bool MARGIN>
+cudaError_t launch_latency(const BrArgs &a, cudaStream_t s) {
+    constexpr int G = 2 * L;
+    const size_t smem = 2 * kN * 4 + (size_t)G * kBskChunkBytes + (size_t)G * (kX1Slots + kX2Slots) * 16 + 64 + align16((a.n + 1) * 2);
+    auto kern = blind_rotate_latency_kernel<L, MARGIN>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<a.B, G * kGroupThreads, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
 template <int KCT, bool USE_TMA, bool MARGIN>
 cudaError_t launch_variant(const BrArgs &a, cudaStream_t s) {
     using Lay = Layout<KCT>;
@@ -464,6 +607,17 @@ cudaError_t launch_kct(const BrArgs &a, bool tma, bool margin, cudaStream_t s) {
 
 cudaError_t launch_blind_rotate(const BrArgs &a, const BrTuning &tune, bool track_margin, cudaStream_t s, uint64_t *launches) {
     if (a.B == 0) return cudaSuccess;
+    const unsigned sm_total = tune.sm_count > 0 ? (unsigned)tune.sm_count : 148u;
+    // latency mode: every ciphertext gets an SM of its own; only where the external product is exact
+    // (so the different summation order cannot change a rounded coefficient)
+    if (tune.latency_mode != 0 && tune.kct <= 0 && a.B <= sm_total && !a.wide_round && a.L >= 1 && a.L <= 3) {
+        if (launches) (*launches)++;
+        switch (a.L) {
+            case 1: return track_margin ? launch_latency<1, true>(a, s) : launch_latency<1, false>(a, s);
+            case 2: return track_margin ? launch_latency<2, true>(a, s) : launch_latency<2, false>(a, s);
+            default: return track_margin ? launch_latency<3, true>(a, s) : launch_latency<3, false>(a, s);
+        }
+    }
     int kct = tune.kct;
     if (kct <= 0) {
         // minimise (number of CTA waves) x (time of one CTA at that width); CTA times measured on B200 at n = 700

@@ -492,6 +492,7 @@ int tfhe_b200_set_tuning(tfhe_b200_ctx *c, const char *key, int value) {
     if (!c || !key) return TFHE_B200_ERR_INVALID;
     if (!strcmp(key, "kct")) c->tune.kct = value;
     else if (!strcmp(key, "use_tma")) c->tune.use_tma = value;
+    else if (!strcmp(key, "latency_mode")) c->tune.latency_mode = value;
     else if (!strcmp(key, "timing")) c->timing = value != 0;
     else if (!strcmp(key, "ks_tile")) g_ks_tile_override = value;
     else if (!strcmp(key, "max_chunk")) c->max_chunk = value > 0 ? (size_t)value : c->max_chunk;

@@ -31,6 +31,7 @@ struct BrTuning {
     int kct = 0;        // ciphertexts per CTA (0 = default)
     int use_tma = 1;    // stream key chunks with cp.async.bulk + mbarrier (0: direct global loads)
     int sm_count = 0;   // SMs of the target device (wave-quantisation aware choice of kct)
+    int latency_mode = 1;   // batches <= sm_count: one CTA per ciphertext, transforms of an iteration in parallel
 };
 
 // returns cudaSuccess or the launch error; *launches += kernels launched
