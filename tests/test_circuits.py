@@ -97,3 +97,31 @@ def test_adder_full_size_1024_instances():
         assert (total == x + y).all() and gates == 81920 and levels == 33
     finally:
         ctx.close()
+
+
+@pytest.mark.gpu
+def test_device_resident_adder_equals_host_level_version():
+    import torch
+    import tfhe_b200
+    from tfhe_b200 import circuits, hostkeys as HK
+    params = tfhe_b200.PARAM_SETS["128"]
+    sk, ck = HK.gen_cloud_key(params, seed=2)
+    ctx = tfhe_b200.Context(params, devices=[0])
+    try:
+        ctx.load_cloud_key(ck)
+        rng = np.random.default_rng(9)
+        W, B = 16, 200
+        x = rng.integers(0, 2**16, B); y = rng.integers(0, 2**16, B)
+        enc = lambda bits: np.stack([HK.encrypt_bools(bits[i], params, sk, rng) for i in range(W)])
+        ca, cb = enc(circuits.to_bits(x, W)), enc(circuits.to_bits(y, W))
+        cin = HK.encrypt_bools(np.zeros(B, np.uint8), params, sk, rng)
+        sums_h, carry_h, _, _ = circuits.ripple_carry_add(ctx, ca, cb, cin)
+        t = lambda a: torch.from_numpy(a.view(np.int32)).cuda()
+        sums_d, carry_d = circuits.ripple_carry_add_device(ctx, t(ca), t(cb), t(cin))
+        assert (sums_d.cpu().numpy().view(np.uint32) == sums_h).all()
+        assert (carry_d.cpu().numpy().view(np.uint32) == carry_h).all()
+        dec = np.stack([HK.decrypt_bools(sums_h[i], sk) for i in range(W)])
+        total = circuits.from_bits(dec) + (HK.decrypt_bools(carry_h, sk).astype(np.uint64) << np.uint64(W))
+        assert (total == x + y).all()
+    finally:
+        ctx.close()

@@ -1,0 +1,48 @@
+"""Host-side lut mirror (encoder / generator / LookupTable) against the oracle's restatement, and bootstrapLut on GPU."""
+import numpy as np
+import pytest
+
+from conftest import keys_for
+from oracle import oracle as O
+
+
+def test_lut_generator_matches_oracle():
+    from tfhe_b200 import lut
+    orc = O.Oracle("128")
+    for m in (2, 3, 4, 8, 16, 32):
+        gen = lut.Generator(m)
+        for name, f in (("id", lambda x: x), ("inc", lambda x: (x + 1) % m), ("sq", lambda x: (x * x) % m), ("not", lambda x: m - 1 - x)):
+            table = np.array([f(x) for x in range(m)], np.uint32)
+            assert (gen.generate_lookup_table(f).poly == orc.lut_generate(table, m)).all(), (m, name)
+        enc = lut.Encoder(m)
+        for x in range(m):
+            assert enc.encode(x) == O.lut_encode(x, m) and enc.decode(enc.encode(x)) == x == O.lut_decode(enc.encode(x), m)
+    t = lut.LookupTable()
+    assert t.is_empty()                                   # lookup_table.zig "lookup table creation"
+    t.poly[1, 0] = 42
+    u = lut.LookupTable(); u.copy_from(t)
+    assert not u.is_empty() and u.poly[1, 0] == 42        # "lookup table copy"
+    u.clear()
+    assert u.is_empty()
+    assert lut._div_round(7, 2) == 4 and lut._div_round(1024, 8) == 128   # generator.zig "div round"
+
+
+@pytest.mark.gpu
+def test_bootstrap_lut_on_gpu():
+    import tfhe_b200
+    from tfhe_b200 import lut
+    orc = O.Oracle("128"); k = keys_for("128")
+    c = tfhe_b200.Context("128", devices=[0])
+    try:
+        c.load_key(k.bsk, k.ksk, k.offset)
+        m = 4
+        msgs = np.arange(12, dtype=np.uint32) % m
+        ct = orc.encrypt_lwe_messages(msgs, m, k, seed=77)
+        gen = lut.Generator(m)
+        table = lut.Generator(m).generate_lookup_table(lambda x: (3 * x + 1) % m)
+        out = lut.bootstrap_lut(c, ct, table)
+        assert (orc.decrypt_lwe_messages(out, m, k) == (3 * msgs + 1) % m).all()
+        assert (out == orc.bootstrap_batch(ct, k, table.poly)).all()
+        assert (lut.bootstrap_lut(c, ct[0], table) == out[0]).all()
+    finally:
+        c.close()

@@ -51,3 +51,38 @@ def ripple_carry_add(ctx: Context, a_bits: np.ndarray, b_bits: np.ndarray, cin: 
         gates += 3 * B
         levels += 2
     return sums, carry, gates, levels
+
+
+def ripple_carry_add_device(ctx: Context, d_a, d_b, d_cin, dev: int = 0):
+    """Same circuit with every ciphertext resident on the GPU between levels:
+    d_a, d_b: torch int32 tensors [W][B][n+1] on the context's device `dev`, d_cin: [B][n+1].
+    All work (level gathers and the K1/K2 launches) is enqueued on the library's stream; nothing returns to the host
+    until the caller reads the result.  Returns (sum_bits [W][B][n+1], carry [B][n+1]) as torch tensors."""
+    import torch
+
+    W, B, w = d_a.shape
+    stream = torch.cuda.ExternalStream(ctx.stream(dev), device=d_a.device)
+    with torch.cuda.stream(stream):
+        a_flat = d_a.reshape(W * B, w).contiguous()
+        b_flat = d_b.reshape(W * B, w).contiguous()
+        a_xor_b = torch.empty_like(a_flat)
+        a_and_b = torch.empty_like(a_flat)
+        ctx.gate_batch_device(dev, XOR, None, a_flat.data_ptr(), b_flat.data_ptr(), a_xor_b.data_ptr(), W * B)
+        ctx.gate_batch_device(dev, AND, None, a_flat.data_ptr(), b_flat.data_ptr(), a_and_b.data_ptr(), W * B)
+        a_xor_b = a_xor_b.view(W, B, w)
+        a_and_b = a_and_b.view(W, B, w)
+        ops = torch.cat([torch.full((B,), AND, dtype=torch.int32), torch.full((B,), XOR, dtype=torch.int32)]).to(d_a.device)
+        x2 = torch.empty((2 * B, w), dtype=torch.int32, device=d_a.device)
+        c2 = torch.empty_like(x2)
+        lvl = torch.empty_like(x2)
+        sums = torch.empty_like(d_a)
+        carry = d_cin.contiguous().clone()
+        for i in range(W):
+            x2[:B].copy_(a_xor_b[i]); x2[B:].copy_(a_xor_b[i])
+            c2[:B].copy_(carry); c2[B:].copy_(carry)
+            ctx.gate_batch_device(dev, 0, ops.data_ptr(), x2.data_ptr(), c2.data_ptr(), lvl.data_ptr(), 2 * B)
+            sums[i].copy_(lvl[B:])
+            ctx.gate_batch_device(dev, OR, None, a_and_b[i].data_ptr(), lvl.data_ptr(), carry.data_ptr(), B)
+        # keep every temporary alive until the stream has consumed it
+        stream.synchronize()
+    return sums, carry
