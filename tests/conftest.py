@@ -21,6 +21,18 @@ def pytest_configure(config):
 from oracle import oracle as O  # noqa: E402
 
 
+def _ensure_native_artifacts():
+    """A fresh checkout has no .so files (they are git-ignored): build them once (nvcc cross-compiles without a GPU)."""
+    lib = os.path.join(ROOT, "zig-tfhe_b200", "libtfhe_b200.so")
+    if not os.path.exists(lib):
+        import __graft_entry__ as entry
+        entry.build_cuda()
+    O.build()
+
+
+_ensure_native_artifacts()
+
+
 @pytest.fixture(scope="session")
 def orc128():
     return O.Oracle("128")
