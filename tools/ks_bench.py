@@ -20,8 +20,9 @@ lv1 = torch.randint(-2**31, 2**31 - 1, (B, 1025), dtype=torch.int32, device="cud
 out = torch.empty((B, 701), dtype=torch.int32, device="cuda")
 stream = torch.cuda.ExternalStream(ctx.stream(0))
 ref = None
-for tile in (16, 8, 4, 32):
+for tile, vec in ((8, 1), (8, 2), (4, 2), (4, 1), (16, 1)):
     ctx.set_tuning("ks_tile", tile)
+    ctx.set_tuning("ks_vec", vec)
     for _ in range(2):
         ctx.keyswitch_batch_device(0, lv1.data_ptr(), out.data_ptr(), B)
     ctx.sync()
@@ -35,5 +36,5 @@ for tile in (16, 8, 4, 32):
     o = out.cpu().numpy()
     if ref is None:
         ref = o.copy()
-    print(f"tile={tile:2d} B={B} K2={ms:.2f} ms  ({B / ms * 1e3:.0f} keyswitch/s)  same_bits={bool((o == ref).all())}", flush=True)
+    print(f"tile={tile:2d} vec={vec} B={B} K2={ms:.2f} ms  ({B / ms * 1e3:.0f} keyswitch/s)  same_bits={bool((o == ref).all())}", flush=True)
 ctx.close()

@@ -495,6 +495,7 @@ int tfhe_b200_set_tuning(tfhe_b200_ctx *c, const char *key, int value) {
     else if (!strcmp(key, "latency_mode")) c->tune.latency_mode = value;
     else if (!strcmp(key, "timing")) c->timing = value != 0;
     else if (!strcmp(key, "ks_tile")) g_ks_tile_override = value;
+    else if (!strcmp(key, "ks_vec")) g_ks_vec_override = value;
     else if (!strcmp(key, "max_chunk")) c->max_chunk = value > 0 ? (size_t)value : c->max_chunk;
     else return fail(c, TFHE_B200_ERR_INVALID, "unknown tuning key %s", key);
     return 0;

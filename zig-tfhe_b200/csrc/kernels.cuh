@@ -49,6 +49,7 @@ struct KsArgs {
 };
 cudaError_t launch_keyswitch(const KsArgs &a, int sm_count, cudaStream_t s, uint64_t *launches);
 extern int g_ks_tile_override;
+extern int g_ks_vec_override;
 
 // one-time key re-layout kernels
 cudaError_t launch_permute_bsk(const double *ref_bsk, cplx *out, int n, int L, cudaStream_t s, uint64_t *launches);

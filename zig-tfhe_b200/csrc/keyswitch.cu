@@ -27,14 +27,17 @@ __device__ __forceinline__ void sub4(uint4 &a, const uint4 &r) {
 
 // BASEBIT = 2 fast path (80/110/128-bit and UINT1 sets): 3 rows per (i,j) held in registers.
 // BASEBIT = 0: generic base, row fetched per ciphertext.
-template <int CT, int BASEBIT>
+// V = uint4 vectors per thread (thread `col` owns columns 4*col.. and, for V = 2, 4*(col + pitch4/2)..): the digit
+// decode + warp-uniform branch of every (ciphertext, i, j) is amortised over 4*V subtractions.
+template <int CT, int BASEBIT, int V>
 __global__ void __launch_bounds__(320) keyswitch_kernel(const KsArgs P, int i_per_split, int use_atomics) {
     extern __shared__ uint32_t abar[];   // [CT][i_per_split]
     const int n = P.n, t = P.iks_t;
     const int basebit = BASEBIT ? BASEBIT : P.basebit;
     const int rows_per_pair = (1 << basebit) - 1;
     const int pitch4 = P.pitch >> 2;
-    const int col = threadIdx.x;                       // uint4 column
+    const int half4 = (pitch4 + V - 1) / V;            // uint4 columns per vector slot
+    const int col = threadIdx.x;                       // first uint4 column of this thread
     const size_t ct0 = (size_t)blockIdx.x * CT;
     const int i0 = blockIdx.y * i_per_split;
     const int i1 = min(kN, i0 + i_per_split);
@@ -48,35 +51,57 @@ __global__ void __launch_bounds__(320) keyswitch_kernel(const KsArgs P, int i_pe
         abar[c * i_per_split + i] = (ct < P.B) ? P.lv1[ct * (size_t)(kN + 1) + i0 + i] + prec_offset : 0u;
     }
     __syncthreads();
-    if (col >= pitch4) return;
-
-    uint4 acc[CT];
+    if (col >= half4) return;
+    bool live[V];
 #pragma unroll
-    for (int c = 0; c < CT; c++) acc[c] = make_uint4(0u, 0u, 0u, 0u);
+    for (int v = 0; v < V; v++) live[v] = col + v * half4 < pitch4;
+
+    uint4 acc[CT][V];
+#pragma unroll
+    for (int c = 0; c < CT; c++)
+#pragma unroll
+        for (int v = 0; v < V; v++) acc[c][v] = make_uint4(0u, 0u, 0u, 0u);
 
     const uint4 *ksk4 = reinterpret_cast<const uint4 *>(P.ksk);
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
     for (int i = i0; i < i1; i++) {
         uint32_t ab[CT];
 #pragma unroll
         for (int c = 0; c < CT; c++) ab[c] = abar[c * i_per_split + (i - i0)];
         const uint4 *rowp = ksk4 + ((size_t)i * t) * rows_per_pair * pitch4 + col;
-#pragma unroll 3
         for (int j = 0; j < t; j++, rowp += (size_t)rows_per_pair * pitch4) {
             const int sh = 32 - (j + 1) * basebit;
             if (BASEBIT == 2) {
-                const uint4 r1 = __ldg(rowp), r2 = __ldg(rowp + pitch4), r3 = __ldg(rowp + 2 * pitch4);
+                uint4 r1[V], r2[V], r3[V];
+#pragma unroll
+                for (int v = 0; v < V; v++) {
+                    r1[v] = live[v] ? __ldg(rowp + v * half4) : zero4;
+                    r2[v] = live[v] ? __ldg(rowp + v * half4 + pitch4) : zero4;
+                    r3[v] = live[v] ? __ldg(rowp + v * half4 + 2 * pitch4) : zero4;
+                }
 #pragma unroll
                 for (int c = 0; c < CT; c++) {
                     const uint32_t k = (ab[c] >> sh) & 3u;     // warp-uniform
-                    if (k == 1u) sub4(acc[c], r1);
-                    else if (k == 2u) sub4(acc[c], r2);
-                    else if (k == 3u) sub4(acc[c], r3);
+                    if (k == 1u) {
+#pragma unroll
+                        for (int v = 0; v < V; v++) sub4(acc[c][v], r1[v]);
+                    } else if (k == 2u) {
+#pragma unroll
+                        for (int v = 0; v < V; v++) sub4(acc[c][v], r2[v]);
+                    } else if (k == 3u) {
+#pragma unroll
+                        for (int v = 0; v < V; v++) sub4(acc[c][v], r3[v]);
+                    }
                 }
             } else {
 #pragma unroll
                 for (int c = 0; c < CT; c++) {
                     const uint32_t k = (ab[c] >> sh) & kmask;
-                    if (k != 0u) sub4(acc[c], __ldg(rowp + (size_t)(k - 1u) * pitch4));
+                    if (k != 0u) {
+#pragma unroll
+                        for (int v = 0; v < V; v++)
+                            if (live[v]) sub4(acc[c][v], __ldg(rowp + v * half4 + (size_t)(k - 1u) * pitch4));
+                    }
                 }
             }
         }
@@ -87,34 +112,38 @@ __global__ void __launch_bounds__(320) keyswitch_kernel(const KsArgs P, int i_pe
     for (int c = 0; c < CT; c++) {
         const size_t ct = ct0 + c;
         if (ct >= P.B) break;
-        uint32_t vals[4] = {acc[c].x, acc[c].y, acc[c].z, acc[c].w};
         uint32_t *o = P.lv0 + ct * (size_t)(n + 1);
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const int x = col * 4 + e;
-            if (x > n) continue;
-            uint32_t v = vals[e];
-            if (x == n && blockIdx.y == 0) v += P.lv1[ct * (size_t)(kN + 1) + kN];
-            if (use_atomics) atomicAdd(&o[x], v);
-            else o[x] = v;
+        for (int v = 0; v < V; v++) {
+            const uint32_t vals[4] = {acc[c][v].x, acc[c][v].y, acc[c][v].z, acc[c][v].w};
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int x = (col + v * half4) * 4 + e;
+                if (!live[v] || x > n) continue;
+                uint32_t val = vals[e];
+                if (x == n && blockIdx.y == 0) val += P.lv1[ct * (size_t)(kN + 1) + kN];
+                if (use_atomics) atomicAdd(&o[x], val);
+                else o[x] = val;
+            }
         }
     }
 }
 
-template <int CT>
+template <int CT, int V>
 cudaError_t launch_ct(const KsArgs &a, int splits, cudaStream_t s) {
     const int i_per_split = (kN + splits - 1) / splits;
     const size_t smem = (size_t)CT * i_per_split * sizeof(uint32_t);
     const dim3 grid((a.B + CT - 1) / CT, splits);
-    const int threads = (((a.pitch >> 2) + 31) / 32) * 32;
+    const int pitch4 = a.pitch >> 2;
+    const int threads = ((((pitch4 + V - 1) / V) + 31) / 32) * 32;
     cudaError_t e;
     if (a.basebit == 2) {
-        auto k = keyswitch_kernel<CT, 2>;
+        auto k = keyswitch_kernel<CT, 2, V>;
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         k<<<grid, threads, smem, s>>>(a, i_per_split, splits > 1);
     } else {
-        auto k = keyswitch_kernel<CT, 0>;
+        auto k = keyswitch_kernel<CT, 0, V>;
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         k<<<grid, threads, smem, s>>>(a, i_per_split, splits > 1);
@@ -151,6 +180,7 @@ __global__ void extract2_kernel(const uint32_t *lv1, uint32_t *out, uint32_t B, 
 }  // namespace
 
 int g_ks_tile_override = 0;   // tuning knob (tests/bench): ciphertexts per CTA, 0 = automatic
+int g_ks_vec_override = 0;    // 1 or 2 uint4 per thread, 0 = automatic
 
 cudaError_t launch_keyswitch(const KsArgs &a, int sm_count, cudaStream_t s, uint64_t *launches) {
     if (a.B == 0) return cudaSuccess;
@@ -169,10 +199,12 @@ cudaError_t launch_keyswitch(const KsArgs &a, int sm_count, cudaStream_t s, uint
         if (e != cudaSuccess) return e;
     }
     if (launches) (*launches)++;
+    // measured at B = 65,536 (tools/ks_bench.py): tile 8 x 1 vector 60 ms, tile 8 x 2 vectors 79 ms -> one uint4 per thread
+    const bool wide = g_ks_vec_override == 2;
     switch (ct) {
-        case 16: return launch_ct<16>(a, splits, s);
-        case 8: return launch_ct<8>(a, splits, s);
-        default: return launch_ct<4>(a, splits, s);
+        case 16: return launch_ct<16, 1>(a, splits, s);
+        case 8: return wide ? launch_ct<8, 2>(a, splits, s) : launch_ct<8, 1>(a, splits, s);
+        default: return wide ? launch_ct<4, 2>(a, splits, s) : launch_ct<4, 1>(a, splits, s);
     }
 }
 
