@@ -203,3 +203,29 @@ def test_other_sets_decrypt(name):
     a = np.array([0, 1], np.uint8); b = np.array([1, 1], np.uint8)
     out = orc.gate_batch(O.NAND, orc.encrypt_bools(a, keys, 1), orc.encrypt_bools(b, keys, 2), keys)
     assert (orc.decrypt_bools(out, keys) == 1 - (a & b)).all()
+
+
+def test_key_material_shapes_and_constants(orc128, keys128):
+    """key.zig:214-276 "secret key generation", "decomposition offset generation", "test vector generation",
+    "key switching key generation"; trlwe.zig:273 "trlwe fft representation" """
+    assert set(np.unique(keys128.s0)) <= {0, 1} and set(np.unique(keys128.s1)) <= {0, 1}
+    assert keys128.s0.any() and keys128.s1.any()
+    assert keys128.offset == 0x82080000 != 0                        # sum_i 32 * 2^(32 - 6(i+1)), key.zig:121-131
+    assert (keys128.testvec[0] == 0).all() and (keys128.testvec[1] == 0x20000000).all()
+    assert keys128.ksk.shape == (1024 * 9 * 4, 701) and keys128.bsk.shape == (700, 6, 2, 1024)
+    assert (keys128.ksk.reshape(1024, 9, 4, 701)[:, :, 0, :] == 0).all()   # k = 0 rows never written (key.zig:159)
+    # a BSK row is TRGSW(s0_i) in FFT form: transforming back gives integers (exact round trip)
+    back, m = O.fft1024(keys128.bsk[3, 0, 0], with_margin=True)
+    assert m < 1e-3 and (O.ifft1024(back) == keys128.bsk[3, 0, 0]).all()
+    for name, off in (("80", 0x82080000), ("uint1", 0x80200000), ("uint4", 0x80000000)):
+        assert O.Oracle(name).keygen.__self__ is not None
+        import ctypes as C
+        assert int(O.lib().orc_decomposition_offset(C.byref(O.Oracle(name).p))) == off
+
+
+def test_tlwe_lwe_message_encoding(orc128, keys128):
+    """tlwe.zig:370 "tlwe lwe message encoding" (the reference only demands 8 of 10)"""
+    ct = orc128.encrypt_lwe_messages(np.full(10, 2, np.uint32), 4, keys128, seed=123)
+    assert (orc128.decrypt_lwe_messages(ct, 4, keys128) == 2).all()
+    bits = np.array([1, 0, 1, 1, 0], np.uint8)
+    assert (orc128.decrypt_bools(orc128.encrypt_bools(bits, keys128, 9), keys128) == bits).all()   # tlwe.zig:300
