@@ -128,6 +128,11 @@ int tfhe_b200_keyswitch_batch(tfhe_b200_ctx *ctx, const uint32_t *lv1, uint32_t 
 /* trlwe.sampleExtractIndex(., 0) (src/trlwe.zig:146-162) fused after the blind rotation:
  * in [B][n+1] -> lv1 [B][N+1] (parity tap between blind rotation and key switch). */
 int tfhe_b200_blind_rotate_extract_batch(tfhe_b200_ctx *ctx, const uint32_t *in, uint32_t *lv1_out, size_t B);
+/* proxy_reenc.ProxyReencryptionKey + reencryptTLWELv0 (src/proxy_reenc.zig:123-306) over a batch: the same digit-gather-
+ * subtract as the key switch with source dimension n.  key: uint32_t[n*t*base][n+1], row = base*t*i + base*j + k
+ * (k = 0 rows ignored); in/out [B][n+1]. */
+int tfhe_b200_load_reencryption_key(tfhe_b200_ctx *ctx, const uint32_t *key, int basebit, int t);
+int tfhe_b200_reencrypt_batch(tfhe_b200_ctx *ctx, const uint32_t *in, uint32_t *out, size_t B);
 /* Gates.notGate / copy (src/gates.zig:131-141): no bootstrap, out = -a. */
 int tfhe_b200_not_batch(tfhe_b200_ctx *ctx, const uint32_t *a, uint32_t *out, size_t B);
 

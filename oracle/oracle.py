@@ -316,6 +316,22 @@ class Oracle:
         lib().orc_keyswitch_batch(self._pp, _p(v), _p(out), C.c_size_t(B), _p(keys.ksk), C.c_int(nthreads or hardware_threads()))
         return out
 
+    def gen_reenc_key(self, key_from, key_to, seed=3, basebit=None, t=None):
+        basebit = self.basebit if basebit is None else basebit
+        t = self.iks_t if t is None else t
+        out = np.empty((self.n * t * (1 << basebit), self.n + 1), np.uint32)
+        lib().orc_gen_reenc_key(self._pp, C.c_uint64(seed), _p(_u32(key_from)), _p(_u32(key_to)), C.c_int(basebit), C.c_int(t), _p(out))
+        return out
+
+    def reencrypt(self, ct, key, basebit=None, t=None):
+        basebit = self.basebit if basebit is None else basebit
+        t = self.iks_t if t is None else t
+        ct = _u32(ct).reshape(-1, self.n + 1); key = _u32(key)
+        out = np.empty_like(ct)
+        for i in range(ct.shape[0]):
+            lib().orc_reencrypt(self._pp, _p(ct[i]), _p(key), C.c_int(basebit), C.c_int(t), _p(out[i]))
+        return out
+
     def lut_generate(self, table, modulus):
         t = _u32(table); out = np.empty((2, N), np.uint32)
         lib().orc_lut_generate(self._pp, _p(t), C.c_uint32(modulus), _p(out)); return out

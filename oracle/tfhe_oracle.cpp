@@ -681,6 +681,39 @@ void orc_keyswitch_batch(const orc_params *p, const uint32_t *lv1, uint32_t *lv0
     });
 }
 
+void orc_gen_reenc_key(const orc_params *p, uint64_t seed, const uint32_t *key_from, const uint32_t *key_to, int basebit, int t, uint32_t *out) {
+    const int n = p->n;
+    const size_t base = (size_t)1 << basebit;
+    std::memset(out, 0, (size_t)n * t * base * (n + 1) * sizeof(uint32_t));      // proxy_reenc.zig:220-222
+    par_for((size_t)n, std::max(1, orc_hardware_threads()), [&](size_t i) {
+        Rng rng(seed * 0x9e3779b97f4a7c15ULL + 0x5000000ULL + i);
+        for (int j = 0; j < t; j++)
+            for (size_t k = 1; k < base; k++) {                                   // proxy_reenc.zig:225-241
+                const double pv = ((double)k * (double)key_from[i]) / (double)((uint32_t)1 << ((j + 1) * basebit));
+                const size_t idx = (base * t * i) + (base * j) + k;
+                tlwe_encrypt_f64(rng, pv, p->alpha_lv0, key_to, n, out + idx * (size_t)(n + 1));
+            }
+    });
+}
+
+void orc_reencrypt(const orc_params *p, const uint32_t *ct, const uint32_t *key, int basebit, int t, uint32_t *res) {
+    const int n = p->n;
+    const size_t base = (size_t)1 << basebit;
+    for (int x = 0; x < n; x++) res[x] = 0;
+    res[n] = ct[n];                                                               // proxy_reenc.zig:276
+    const uint32_t prec_offset = 1u << (32 - (1 + basebit * t));                  // proxy_reenc.zig:279
+    for (int i = 0; i < n; i++) {
+        const uint32_t a_bar = ct[i] + prec_offset;
+        for (int j = 0; j < t; j++) {
+            const uint32_t k = (a_bar >> (32 - (j + 1) * basebit)) & (uint32_t)(base - 1);
+            if (k != 0) {
+                const uint32_t *row = key + ((base * t * (size_t)i) + (base * (size_t)j) + k) * (size_t)(n + 1);
+                for (int x = 0; x <= n; x++) res[x] -= row[x];                    // proxy_reenc.zig:299-301
+            }
+        }
+    }
+}
+
 uint32_t orc_lut_encode(uint32_t message, uint32_t modulus) {               // encoder.zig:66-73
     const double scale = 1.0 / (2.0 * (double)modulus);                     // encoder.zig:35
     return f64_to_torus((double)(message % modulus) * scale);

@@ -30,6 +30,7 @@ struct Device {
     cudaStream_t stream = nullptr;
     cplx *bsk = nullptr;
     uint32_t *ksk = nullptr;
+    uint32_t *reenc = nullptr;        // proxy re-encryption key, same device layout as ksk with N -> n
     cplx *tw2 = nullptr, *tw3 = nullptr;
     double *exact_tables = nullptr;   // make_exact_tables(), exact mode
     double *bsk_ref = nullptr;        // bootstrapping key in the reference layout (exact mode reads it as is)
@@ -47,7 +48,8 @@ struct tfhe_b200_ctx {
     std::string err;
     int mode = TFHE_B200_MODE_FAST;
     bool track_margin = false;
-    bool has_key = false, has_ksk = false;
+    bool has_key = false, has_ksk = false, has_reenc = false;
+    int reenc_basebit = 0, reenc_t = 0;
     uint32_t offset = 0;
     int ksk_pitch = 0;
     BrTuning tune;
@@ -122,7 +124,7 @@ int run_device(tfhe_b200_ctx *c, Device &d, int op, const int32_t *d_ops, const 
     if (c->timing) CU(c, cudaEventRecord(d.ev[1], d.stream));
     if (d_lv0) {
         if (!c->has_ksk) return fail(c, TFHE_B200_ERR_NO_KEY, "no key-switching key loaded");
-        KsArgs K{lv1, d_lv0, d.ksk, (uint32_t)B, c->prm.n, c->prm.basebit, c->prm.iks_t, c->ksk_pitch};
+        KsArgs K{lv1, d_lv0, d.ksk, (uint32_t)B, c->prm.n, c->prm.basebit, c->prm.iks_t, c->ksk_pitch, kN};
         CU(c, launch_keyswitch(K, d.sm_count, d.stream, &c->launches));
     }
     if (c->timing) {
@@ -250,7 +252,7 @@ int upload_key_device(tfhe_b200_ctx *c, Device &d, const double *src_bsk, bool b
             d_refk = stg;
         }
         CU(c, cudaMalloc(&d.ksk, (size_t)kN * p.iks_t * (base - 1) * c->ksk_pitch * 4));
-        CU(c, launch_repack_ksk(d_refk, ksk_stride_u32, d.ksk, p.n, p.basebit, p.iks_t, c->ksk_pitch, d.stream, &c->launches));
+        CU(c, launch_repack_ksk(d_refk, ksk_stride_u32, d.ksk, p.n, p.basebit, p.iks_t, c->ksk_pitch, kN, d.stream, &c->launches));
         CU(c, cudaStreamSynchronize(d.stream));
         if (stg) CU(c, cudaFree(stg));
     }
@@ -312,7 +314,7 @@ void tfhe_b200_destroy(tfhe_b200_ctx *c) {
     for (Device &d : c->devs) {
         cudaSetDevice(d.id);
         if (d.stream) cudaStreamSynchronize(d.stream);
-        for (void *p : {(void *)d.bsk, (void *)d.ksk, (void *)d.tw2, (void *)d.tw3, (void *)d.exact_tables, (void *)d.bsk_ref, (void *)d.margin_bits, d.a.p, d.b.p,
+        for (void *p : {(void *)d.bsk, (void *)d.ksk, (void *)d.reenc, (void *)d.tw2, (void *)d.tw3, (void *)d.exact_tables, (void *)d.bsk_ref, (void *)d.margin_bits, d.a.p, d.b.p,
                         d.out.p, d.lv1.p, d.ops.p, d.tv.p, d.trlwe.p})
             if (p) cudaFree(p);
         for (cudaEvent_t e : d.ev) if (e) cudaEventDestroy(e);
@@ -397,9 +399,53 @@ int tfhe_b200_keyswitch_batch(tfhe_b200_ctx *c, const uint32_t *lv1, uint32_t *l
             if (int r = ensure(c, d.lv1, nb * w1 * 4)) return r;
             if (int r = ensure(c, d.out, nb * w0 * 4)) return r;
             CU(c, cudaMemcpyAsync(d.lv1.p, lv1 + off * w1, nb * w1 * 4, cudaMemcpyHostToDevice, d.stream));
-            KsArgs K{(uint32_t *)d.lv1.p, (uint32_t *)d.out.p, d.ksk, (uint32_t)nb, c->prm.n, c->prm.basebit, c->prm.iks_t, c->ksk_pitch};
+            KsArgs K{(uint32_t *)d.lv1.p, (uint32_t *)d.out.p, d.ksk, (uint32_t)nb, c->prm.n, c->prm.basebit, c->prm.iks_t, c->ksk_pitch, kN};
             CU(c, launch_keyswitch(K, d.sm_count, d.stream, &c->launches));
             CU(c, cudaMemcpyAsync(lv0 + off * w0, d.out.p, nb * w0 * 4, cudaMemcpyDeviceToHost, d.stream));
+            CU(c, cudaStreamSynchronize(d.stream));
+        }
+    }
+    return 0;
+}
+
+int tfhe_b200_load_reencryption_key(tfhe_b200_ctx *c, const uint32_t *key, int basebit, int t) {
+    if (!c || !key || basebit < 1 || basebit > 8 || t < 1 || 1 + basebit * t > 32) return fail(c, TFHE_B200_ERR_INVALID, "bad re-encryption key");
+    const int n = c->prm.n, base = 1 << basebit;
+    const size_t rows = (size_t)n * t * base, w = (size_t)n + 1;
+    for (Device &d : c->devs) {
+        CU(c, cudaSetDevice(d.id));
+        uint32_t *stg = nullptr;
+        CU(c, cudaMalloc(&stg, rows * w * 4));
+        CU(c, cudaMemcpyAsync(stg, key, rows * w * 4, cudaMemcpyHostToDevice, d.stream));
+        if (d.reenc) CU(c, cudaFree(d.reenc));
+        CU(c, cudaMalloc(&d.reenc, (size_t)n * t * (base - 1) * c->ksk_pitch * 4));
+        CU(c, launch_repack_ksk(stg, w, d.reenc, n, basebit, t, c->ksk_pitch, n, d.stream, &c->launches));
+        CU(c, cudaStreamSynchronize(d.stream));
+        CU(c, cudaFree(stg));
+    }
+    c->has_reenc = true;
+    c->reenc_basebit = basebit;
+    c->reenc_t = t;
+    return 0;
+}
+
+int tfhe_b200_reencrypt_batch(tfhe_b200_ctx *c, const uint32_t *in, uint32_t *out, size_t B) {
+    if (!c || !in || !out) return fail(c, TFHE_B200_ERR_INVALID, "null buffer");
+    if (!c->has_reenc) return fail(c, TFHE_B200_ERR_NO_KEY, "no proxy re-encryption key loaded");
+    const size_t w = (size_t)c->prm.n + 1;
+    const int nd = (int)c->devs.size();
+    for (int k = 0; k < nd; k++) {
+        Device &d = c->devs[k];
+        const size_t lo = B * k / nd, hi = B * (k + 1) / nd;
+        for (size_t off = lo; off < hi; off += c->max_chunk) {
+            const size_t nb = std::min(c->max_chunk, hi - off);
+            CU(c, cudaSetDevice(d.id));
+            if (int r = ensure(c, d.a, nb * w * 4)) return r;
+            if (int r = ensure(c, d.out, nb * w * 4)) return r;
+            CU(c, cudaMemcpyAsync(d.a.p, in + off * w, nb * w * 4, cudaMemcpyHostToDevice, d.stream));
+            KsArgs K{(uint32_t *)d.a.p, (uint32_t *)d.out.p, d.reenc, (uint32_t)nb, c->prm.n, c->reenc_basebit, c->reenc_t, c->ksk_pitch, c->prm.n};
+            CU(c, launch_keyswitch(K, d.sm_count, d.stream, &c->launches));
+            CU(c, cudaMemcpyAsync(out + off * w, d.out.p, nb * w * 4, cudaMemcpyDeviceToHost, d.stream));
             CU(c, cudaStreamSynchronize(d.stream));
         }
     }
@@ -445,7 +491,7 @@ int tfhe_b200_keyswitch_batch_device(tfhe_b200_ctx *c, int dev, const uint32_t *
     if (!c->has_ksk) return fail(c, TFHE_B200_ERR_NO_KEY, "no key-switching key loaded");
     Device &d = c->devs[dev];
     CU(c, cudaSetDevice(d.id));
-    KsArgs K{d_lv1, d_lv0, d.ksk, (uint32_t)B, c->prm.n, c->prm.basebit, c->prm.iks_t, c->ksk_pitch};
+    KsArgs K{d_lv1, d_lv0, d.ksk, (uint32_t)B, c->prm.n, c->prm.basebit, c->prm.iks_t, c->ksk_pitch, kN};
     CU(c, launch_keyswitch(K, d.sm_count, d.stream, &c->launches));
     return 0;
 }

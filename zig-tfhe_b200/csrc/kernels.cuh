@@ -46,6 +46,7 @@ struct KsArgs {
     const uint32_t *ksk;
     uint32_t B;
     int n, basebit, iks_t, pitch;   // pitch = row length in u32 (multiple of 4)
+    int in_dim;                     // mask length of the source samples: N (key switch) or n (proxy re-encryption)
 };
 cudaError_t launch_keyswitch(const KsArgs &a, int sm_count, cudaStream_t s, uint64_t *launches);
 extern int g_ks_tile_override;
@@ -54,7 +55,7 @@ extern int g_ks_vec_override;
 // one-time key re-layout kernels
 cudaError_t launch_permute_bsk(const double *ref_bsk, cplx *out, int n, int L, cudaStream_t s, uint64_t *launches);
 cudaError_t launch_repack_ksk(const uint32_t *ref_ksk, size_t ref_row_stride_u32, uint32_t *out, int n, int basebit, int iks_t,
-                              int pitch, cudaStream_t s, uint64_t *launches);
+                              int pitch, int in_dim, cudaStream_t s, uint64_t *launches);
 // K3: out = -a over [B][n+1]
 cudaError_t launch_negate(const uint32_t *a, uint32_t *out, size_t count, cudaStream_t s, uint64_t *launches);
 // first n entries + body of an lv1 sample -> TLWELv0-shaped "hybrid" sample (trlwe.zig:165-180)

@@ -1,4 +1,5 @@
-// keyswitch.cu -- K2: batched identity key switching lv1 -> lv0 (integer, bit-exact on any schedule).
+// keyswitch.cu -- K2: batched identity key switching lv1 -> lv0 (integer, bit-exact on any schedule); the same kernel
+// with in_dim = n is the batched proxy re-encryption lv0 -> lv0 (proxy_reenc.reencryptTLWELv0, src/proxy_reenc.zig:267-306).
 //
 // Replaces trgsw.identityKeySwitching (src/trgsw.zig:471-502):
 //   res.b = src.b;  for i < N, j < t:  k = digit_j(src.a[i] + prec_offset);  if k != 0: res -= KSK[i][j][k]
@@ -40,7 +41,8 @@ __global__ void __launch_bounds__(320) keyswitch_kernel(const KsArgs P, int i_pe
     const int col = threadIdx.x;                       // first uint4 column of this thread
     const size_t ct0 = (size_t)blockIdx.x * CT;
     const int i0 = blockIdx.y * i_per_split;
-    const int i1 = min(kN, i0 + i_per_split);
+    const int in_dim = P.in_dim;
+    const int i1 = min(in_dim, i0 + i_per_split);
     const uint32_t prec_offset = 1u << (32 - (1 + basebit * t));   // trgsw.zig:483
     const uint32_t kmask = (1u << basebit) - 1u;
 
@@ -48,7 +50,7 @@ __global__ void __launch_bounds__(320) keyswitch_kernel(const KsArgs P, int i_pe
         const int c = idx / (i1 - i0), i = idx - c * (i1 - i0);
         const size_t ct = ct0 + c;
         // inactive slots: abar = 0 -> every digit is 0 -> nothing subtracted
-        abar[c * i_per_split + i] = (ct < P.B) ? P.lv1[ct * (size_t)(kN + 1) + i0 + i] + prec_offset : 0u;
+        abar[c * i_per_split + i] = (ct < P.B) ? P.lv1[ct * (size_t)(in_dim + 1) + i0 + i] + prec_offset : 0u;
     }
     __syncthreads();
     if (col >= half4) return;
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(320) keyswitch_kernel(const KsArgs P, int i_pe
                 const int x = (col + v * half4) * 4 + e;
                 if (!live[v] || x > n) continue;
                 uint32_t val = vals[e];
-                if (x == n && blockIdx.y == 0) val += P.lv1[ct * (size_t)(kN + 1) + kN];
+                if (x == n && blockIdx.y == 0) val += P.lv1[ct * (size_t)(in_dim + 1) + in_dim];
                 if (use_atomics) atomicAdd(&o[x], val);
                 else o[x] = val;
             }
@@ -131,7 +133,7 @@ __global__ void __launch_bounds__(320) keyswitch_kernel(const KsArgs P, int i_pe
 
 template <int CT, int V>
 cudaError_t launch_ct(const KsArgs &a, int splits, cudaStream_t s) {
-    const int i_per_split = (kN + splits - 1) / splits;
+    const int i_per_split = (a.in_dim + splits - 1) / splits;
     const size_t smem = (size_t)CT * i_per_split * sizeof(uint32_t);
     const dim3 grid((a.B + CT - 1) / CT, splits);
     const int pitch4 = a.pitch >> 2;
@@ -209,8 +211,8 @@ cudaError_t launch_keyswitch(const KsArgs &a, int sm_count, cudaStream_t s, uint
 }
 
 cudaError_t launch_repack_ksk(const uint32_t *ref_ksk, size_t ref_row_stride_u32, uint32_t *out, int n, int basebit, int iks_t,
-                              int pitch, cudaStream_t s, uint64_t *launches) {
-    const int pairs = kN * iks_t;
+                              int pitch, int in_dim, cudaStream_t s, uint64_t *launches) {
+    const int pairs = in_dim * iks_t;
     repack_ksk_kernel<<<pairs, 256, 0, s>>>(ref_ksk, ref_row_stride_u32, out, n, 1 << basebit, pairs, pitch);
     if (launches) (*launches)++;
     return cudaGetLastError();

@@ -105,6 +105,8 @@ def load_library():
         "tfhe_b200_keyswitch_batch": (i32, [vp, vp, vp, sz]),
         "tfhe_b200_blind_rotate_extract_batch": (i32, [vp, vp, vp, sz]),
         "tfhe_b200_not_batch": (i32, [vp, vp, vp, sz]),
+        "tfhe_b200_load_reencryption_key": (i32, [vp, vp, i32, i32]),
+        "tfhe_b200_reencrypt_batch": (i32, [vp, vp, vp, sz]),
         "tfhe_b200_gate_batch_device": (i32, [vp, i32, i32, vp, vp, vp, vp, sz]),
         "tfhe_b200_bootstrap_batch_device": (i32, [vp, i32, vp, vp, sz, vp, i32]),
         "tfhe_b200_blind_rotate_batch_device": (i32, [vp, i32, vp, vp, sz, vp, i32]),
@@ -134,6 +136,7 @@ EXPORTED_SYMBOLS = [
     "tfhe_b200_bootstrap_batch_device", "tfhe_b200_blind_rotate_batch_device", "tfhe_b200_keyswitch_batch_device",
     "tfhe_b200_stream", "tfhe_b200_sync", "tfhe_b200_track_margin", "tfhe_b200_max_round_margin", "tfhe_b200_launch_count",
     "tfhe_b200_set_tuning", "tfhe_b200_measure_fp64_tflops", "tfhe_b200_last_kernel_ms",
+    "tfhe_b200_load_reencryption_key", "tfhe_b200_reencrypt_batch",
 ]
 
 
@@ -268,6 +271,22 @@ class Context:
         lv1 = _u32(lv1, N + 1); B = lv1.shape[0]
         out = np.empty((B, self.n + 1), np.uint32)
         self._check(self.lib.tfhe_b200_keyswitch_batch(self.h, _ptr(lv1), _ptr(out), B))
+        return out
+
+    def load_reencryption_key(self, key, basebit=None, t=None):
+        """proxy_reenc.ProxyReencryptionKey (proxy_reenc.zig:123-252): u32 [n*t*base][n+1]"""
+        p = self.params
+        basebit = p.basebit if basebit is None else basebit
+        t = p.iks_t if t is None else t
+        key = _u32(key)
+        assert key.size == p.n * t * (1 << basebit) * (p.n + 1), "re-encryption key has the wrong size"
+        self._check(self.lib.tfhe_b200_load_reencryption_key(self.h, _ptr(key), basebit, t))
+
+    def reencrypt_batch(self, ct):
+        """proxy_reenc.reencryptTLWELv0 (proxy_reenc.zig:267-306) over a batch"""
+        ct = _u32(ct, self.n + 1)
+        out = np.empty_like(ct)
+        self._check(self.lib.tfhe_b200_reencrypt_batch(self.h, _ptr(ct), _ptr(out), ct.shape[0]))
         return out
 
     def not_batch(self, a):

@@ -46,5 +46,8 @@ pub extern fn tfhe_b200_bootstrap_batch(ctx: *Ctx, in: [*]const u32, out: [*]u32
 pub extern fn tfhe_b200_bootstrap_no_keyswitch_batch(ctx: *Ctx, in: [*]const u32, out: [*]u32, count: usize) c_int;
 pub extern fn tfhe_b200_blind_rotate_batch(ctx: *Ctx, in: [*]const u32, trlwe_out: [*]u32, count: usize, testvec: ?[*]const u32, tv_per_item: c_int) c_int;
 pub extern fn tfhe_b200_keyswitch_batch(ctx: *Ctx, lv1: [*]const u32, lv0: [*]u32, count: usize) c_int;
+/// proxy_reenc.ProxyReencryptionKey / reencryptTLWELv0 (src/proxy_reenc.zig:123-306), batched
+pub extern fn tfhe_b200_load_reencryption_key(ctx: *Ctx, key: [*]const u32, basebit: c_int, t: c_int) c_int;
+pub extern fn tfhe_b200_reencrypt_batch(ctx: *Ctx, in: [*]const u32, out: [*]u32, count: usize) c_int;
 pub extern fn tfhe_b200_not_batch(ctx: *Ctx, a: [*]const u32, out: [*]u32, count: usize) c_int;
 pub extern fn tfhe_b200_sync(ctx: *Ctx) c_int;
