@@ -55,6 +55,7 @@ struct tfhe_b200_ctx {
     BrTuning tune;
     uint64_t launches = 0;
     bool timing = false;
+    int ks_tile = 0, ks_vec = 0;          // key-switch tuning overrides (0 = automatic)
     size_t max_chunk = (size_t)1 << 18;   // ciphertexts per device per launch
 };
 
@@ -124,7 +125,7 @@ int run_device(tfhe_b200_ctx *c, Device &d, int op, const int32_t *d_ops, const 
     if (c->timing) CU(c, cudaEventRecord(d.ev[1], d.stream));
     if (d_lv0) {
         if (!c->has_ksk) return fail(c, TFHE_B200_ERR_NO_KEY, "no key-switching key loaded");
-        KsArgs K{lv1, d_lv0, d.ksk, (uint32_t)B, c->prm.n, c->prm.basebit, c->prm.iks_t, c->ksk_pitch, kN};
+        KsArgs K{lv1, d_lv0, d.ksk, (uint32_t)B, c->prm.n, c->prm.basebit, c->prm.iks_t, c->ksk_pitch, kN, c->ks_tile, c->ks_vec};
         CU(c, launch_keyswitch(K, d.sm_count, d.stream, &c->launches));
     }
     if (c->timing) {
@@ -399,7 +400,7 @@ int tfhe_b200_keyswitch_batch(tfhe_b200_ctx *c, const uint32_t *lv1, uint32_t *l
             if (int r = ensure(c, d.lv1, nb * w1 * 4)) return r;
             if (int r = ensure(c, d.out, nb * w0 * 4)) return r;
             CU(c, cudaMemcpyAsync(d.lv1.p, lv1 + off * w1, nb * w1 * 4, cudaMemcpyHostToDevice, d.stream));
-            KsArgs K{(uint32_t *)d.lv1.p, (uint32_t *)d.out.p, d.ksk, (uint32_t)nb, c->prm.n, c->prm.basebit, c->prm.iks_t, c->ksk_pitch, kN};
+            KsArgs K{(uint32_t *)d.lv1.p, (uint32_t *)d.out.p, d.ksk, (uint32_t)nb, c->prm.n, c->prm.basebit, c->prm.iks_t, c->ksk_pitch, kN, c->ks_tile, c->ks_vec};
             CU(c, launch_keyswitch(K, d.sm_count, d.stream, &c->launches));
             CU(c, cudaMemcpyAsync(lv0 + off * w0, d.out.p, nb * w0 * 4, cudaMemcpyDeviceToHost, d.stream));
             CU(c, cudaStreamSynchronize(d.stream));
@@ -443,7 +444,7 @@ int tfhe_b200_reencrypt_batch(tfhe_b200_ctx *c, const uint32_t *in, uint32_t *ou
             if (int r = ensure(c, d.a, nb * w * 4)) return r;
             if (int r = ensure(c, d.out, nb * w * 4)) return r;
             CU(c, cudaMemcpyAsync(d.a.p, in + off * w, nb * w * 4, cudaMemcpyHostToDevice, d.stream));
-            KsArgs K{(uint32_t *)d.a.p, (uint32_t *)d.out.p, d.reenc, (uint32_t)nb, c->prm.n, c->reenc_basebit, c->reenc_t, c->ksk_pitch, c->prm.n};
+            KsArgs K{(uint32_t *)d.a.p, (uint32_t *)d.out.p, d.reenc, (uint32_t)nb, c->prm.n, c->reenc_basebit, c->reenc_t, c->ksk_pitch, c->prm.n, c->ks_tile, c->ks_vec};
             CU(c, launch_keyswitch(K, d.sm_count, d.stream, &c->launches));
             CU(c, cudaMemcpyAsync(out + off * w, d.out.p, nb * w * 4, cudaMemcpyDeviceToHost, d.stream));
             CU(c, cudaStreamSynchronize(d.stream));
@@ -491,7 +492,7 @@ int tfhe_b200_keyswitch_batch_device(tfhe_b200_ctx *c, int dev, const uint32_t *
     if (!c->has_ksk) return fail(c, TFHE_B200_ERR_NO_KEY, "no key-switching key loaded");
     Device &d = c->devs[dev];
     CU(c, cudaSetDevice(d.id));
-    KsArgs K{d_lv1, d_lv0, d.ksk, (uint32_t)B, c->prm.n, c->prm.basebit, c->prm.iks_t, c->ksk_pitch, kN};
+    KsArgs K{d_lv1, d_lv0, d.ksk, (uint32_t)B, c->prm.n, c->prm.basebit, c->prm.iks_t, c->ksk_pitch, kN, c->ks_tile, c->ks_vec};
     CU(c, launch_keyswitch(K, d.sm_count, d.stream, &c->launches));
     return 0;
 }
@@ -540,8 +541,8 @@ int tfhe_b200_set_tuning(tfhe_b200_ctx *c, const char *key, int value) {
     else if (!strcmp(key, "use_tma")) c->tune.use_tma = value;
     else if (!strcmp(key, "latency_mode")) c->tune.latency_mode = value;
     else if (!strcmp(key, "timing")) c->timing = value != 0;
-    else if (!strcmp(key, "ks_tile")) g_ks_tile_override = value;
-    else if (!strcmp(key, "ks_vec")) g_ks_vec_override = value;
+    else if (!strcmp(key, "ks_tile")) c->ks_tile = value;
+    else if (!strcmp(key, "ks_vec")) c->ks_vec = value;
     else if (!strcmp(key, "max_chunk")) c->max_chunk = value > 0 ? (size_t)value : c->max_chunk;
     else return fail(c, TFHE_B200_ERR_INVALID, "unknown tuning key %s", key);
     return 0;

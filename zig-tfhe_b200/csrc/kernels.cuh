@@ -47,10 +47,9 @@ struct KsArgs {
     uint32_t B;
     int n, basebit, iks_t, pitch;   // pitch = row length in u32 (multiple of 4)
     int in_dim;                     // mask length of the source samples: N (key switch) or n (proxy re-encryption)
+    int tile = 0, vec = 0;          // tuning overrides (0 = automatic): ciphertexts per CTA, uint4 vectors per thread
 };
 cudaError_t launch_keyswitch(const KsArgs &a, int sm_count, cudaStream_t s, uint64_t *launches);
-extern int g_ks_tile_override;
-extern int g_ks_vec_override;
 
 // one-time key re-layout kernels
 cudaError_t launch_permute_bsk(const double *ref_bsk, cplx *out, int n, int L, cudaStream_t s, uint64_t *launches);

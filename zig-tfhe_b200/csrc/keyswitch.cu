@@ -181,9 +181,6 @@ __global__ void extract2_kernel(const uint32_t *lv1, uint32_t *out, uint32_t B, 
 
 }  // namespace
 
-int g_ks_tile_override = 0;   // tuning knob (tests/bench): ciphertexts per CTA, 0 = automatic
-int g_ks_vec_override = 0;    // 1 or 2 uint4 per thread, 0 = automatic
-
 cudaError_t launch_keyswitch(const KsArgs &a, int sm_count, cudaStream_t s, uint64_t *launches) {
     if (a.B == 0) return cudaSuccess;
     if (a.pitch > 320 * 4) return cudaErrorInvalidValue;
@@ -191,7 +188,7 @@ cudaError_t launch_keyswitch(const KsArgs &a, int sm_count, cudaStream_t s, uint
     // measured on B200 at B = 65,536 (tools/ks_bench.py): tile 8 = 61 ms, 16 = 84 ms, 4 = 68 ms, 32 = 178 ms:
     // the kernel is latency-bound, small tiles keep ~7 CTAs per SM resident and the rows hit in L1
     int ct = (a.B >= (uint32_t)(8 * sm_count)) ? 8 : 4;
-    if (g_ks_tile_override == 4 || g_ks_tile_override == 8 || g_ks_tile_override == 16) ct = g_ks_tile_override;
+    if (a.tile == 4 || a.tile == 8 || a.tile == 16) ct = a.tile;
     const int tiles = (a.B + ct - 1) / ct;
     int splits = 1;
     while (tiles * splits < 2 * sm_count && splits < 32) splits *= 2;
@@ -202,7 +199,7 @@ cudaError_t launch_keyswitch(const KsArgs &a, int sm_count, cudaStream_t s, uint
     }
     if (launches) (*launches)++;
     // measured at B = 65,536 (tools/ks_bench.py): tile 8 x 1 vector 60 ms, tile 8 x 2 vectors 79 ms -> one uint4 per thread
-    const bool wide = g_ks_vec_override == 2;
+    const bool wide = a.vec == 2;
     switch (ct) {
         case 16: return launch_ct<16, 1>(a, splits, s);
         case 8: return wide ? launch_ct<8, 2>(a, splits, s) : launch_ct<8, 1>(a, splits, s);
