@@ -21,6 +21,9 @@ ctx = tfhe_b200.Context(params, devices=[0])
 ctx.load_cloud_key(ck)
 if kct:
     ctx.set_tuning("kct", kct)
+for kv in sys.argv[4:]:          # extra tuning keys: pipeline=0 team=2 ...
+    k, v = kv.split("=")
+    ctx.set_tuning(k, int(v))
 ctx.set_tuning("timing", 1)
 for _ in range(reps):
     out = ctx.gate_batch(tfhe_b200.NAND, ca, cb)

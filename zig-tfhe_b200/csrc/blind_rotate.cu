@@ -35,6 +35,8 @@ namespace tfhe_b200 {
 
 namespace {
 
+// Teams of two pay off where they free registers (KCT = 6: 112.9 k vs 90.8 k bootstraps/s at KCT = 4); at KCT <= 4 the
+// wider barriers cost 2 % (measured, profiles/r01_team_probe.log), so the default keeps one ciphertext per warp pair there.
 constexpr int kMaxStages = 4;  // deepest key ring (16 KiB per stage); Layout<KCT>::kStages picks the depth
 
 // Key-ring producer state, live only in thread 0 of the CTA (see header comment).
@@ -52,7 +54,7 @@ struct Producer {
 };
 __device__ __forceinline__ void producer_poll(Producer &pr) {
     if (pr.active && pr.remaining > 0) {
-        if (pr.issued < pr.stages || mbar_try_wait(&pr.empty_bar[pr.stage], pr.phase ^ 1)) {
+        if (pr.issued < pr.stages || mbar_test_wait(&pr.empty_bar[pr.stage], pr.phase ^ 1)) {
             mbar_arrive_expect_tx(&pr.full_bar[pr.stage], kBskChunkBytes);
             bulk_g2s(pr.ring + pr.stage * kBskChunkCplx, pr.src, kBskChunkBytes, &pr.full_bar[pr.stage], pr.policy);
             pr.src += kBskChunkCplx;
@@ -72,14 +74,21 @@ struct Xbuf {
     int flip;     // 0 or kX2Slots
 };
 
-// Pass-2 twiddles of one thread.  FULL: r^1..r^7 resident (28 registers, KCT <= 4);
-// POW: r, r^2, r^4 resident and the rest expanded per pass (12 registers, KCT = 5, 6).
-template <bool POW>
+// Twiddles r^1..r^7 of one thread for one pass.  MODE 0: all seven resident (28 registers, KCT <= 4);
+// MODE 1: r, r^2, r^4 resident and the rest expanded per pass (12 registers); MODE 2: read from a shared-memory
+// table right before use (0 registers; with teams of two the loads of adjacent lanes merge, see the kernel).
+constexpr int kTwFull = 0, kTwPow = 1, kTwSmem = 2;
+template <int MODE>
 struct Tw2 {
-    cplx w[POW ? 3 : 7];
+    cplx w[MODE == kTwFull ? 7 : MODE == kTwPow ? 3 : 1];
+    const cplx *tab;   // MODE 2: &table[this thread's node], powers `stride` apart
+    int stride;
     __device__ __forceinline__ void get(cplx (&out)[7]) const {
-        if (POW) expand_powers(out, w[0], w[1], w[2]);
-        else {
+        if (MODE == kTwPow) expand_powers(out, w[0], w[1], w[2]);
+        else if (MODE == kTwSmem) {
+#pragma unroll
+            for (int p = 0; p < 7; p++) out[p] = tab[p * stride];
+        } else {
 #pragma unroll
             for (int p = 0; p < 7; p++) out[p] = w[p];
         }
@@ -87,9 +96,9 @@ struct Tw2 {
 };
 
 // forward transform, role A registers in -> role C (leaf order) out
-template <bool USE_TMA, bool DBX2, bool POW, bool POW3>
+template <bool USE_TMA, bool DBX2, int POW, int POW3>
 __device__ __forceinline__ void fwd_transform(cplx (&v)[8], Xbuf &xb, const Tw2<POW> &tw2, const Tw2<POW3> &tw3, int hi, int lo,
-                                              int barid, Producer &pr) {
+                                              int barid, Producer &pr, int nthr = kGroupThreads) {
     fwd_pass1(v);
     cplx *x1 = xb.x1;
 #pragma unroll
@@ -105,10 +114,10 @@ __device__ __forceinline__ void fwd_transform(cplx (&v)[8], Xbuf &xb, const Tw2<
     if (USE_TMA) producer_poll(pr);
     cplx *x2 = xb.x2 + (DBX2 ? xb.flip : 0);
     if (DBX2) xb.flip ^= kX2Slots;
-    else bar_sync(barid, kGroupThreads);   // every reader of the previous X2 contents is done
+    else bar_sync(barid, nthr);   // every reader of the previous X2 contents is done
 #pragma unroll
     for (int q = 0; q < 8; q++) x2[x2_slot(lo, q, hi)] = v[q];
-    bar_sync(barid, kGroupThreads);
+    bar_sync(barid, nthr);
 #pragma unroll
     for (int q = 0; q < 8; q++) v[q] = x2[x2_slot(hi, lo, q)];
     {
@@ -119,9 +128,9 @@ __device__ __forceinline__ void fwd_transform(cplx (&v)[8], Xbuf &xb, const Tw2<
 }
 
 // inverse transform, role C (leaf order) in -> role A out: v[p] = c_e, e = 64 p + 8 lo + hi
-template <bool USE_TMA, bool DBX2, bool POW, bool POW3>
+template <bool USE_TMA, bool DBX2, int POW, int POW3>
 __device__ __forceinline__ void inv_transform(cplx (&v)[8], Xbuf &xb, const Tw2<POW> &tw2, const Tw2<POW3> &tw3, int hi, int lo,
-                                              int barid, Producer &pr) {
+                                              int barid, Producer &pr, int nthr = kGroupThreads) {
     {
         cplx w[7];
         tw3.get(w);
@@ -130,10 +139,10 @@ __device__ __forceinline__ void inv_transform(cplx (&v)[8], Xbuf &xb, const Tw2<
     if (USE_TMA) producer_poll(pr);
     cplx *x2 = xb.x2 + (DBX2 ? xb.flip : 0);
     if (DBX2) xb.flip ^= kX2Slots;
-    else bar_sync(barid, kGroupThreads);
+    else bar_sync(barid, nthr);
 #pragma unroll
     for (int q = 0; q < 8; q++) x2[x2_slot(hi, lo, q)] = v[q];
-    bar_sync(barid, kGroupThreads);
+    bar_sync(barid, nthr);
 #pragma unroll
     for (int q = 0; q < 8; q++) v[q] = x2[x2_slot(lo, q, hi)];
     {
@@ -191,26 +200,33 @@ __device__ __forceinline__ void round_accumulate(const cplx (&v)[8], uint32_t *a
 __host__ __device__ constexpr int align16(int x) { return (x + 15) & ~15; }
 
 // shared-memory footprint of one ciphertext group
-template <int KCT>
+template <int KCT, int TEAM = 1>
 struct Layout {
-    static constexpr bool kTw2Pow = KCT > 4;    // 168-register budget: keep r, r^2, r^4 of pass 2 and expand per pass
-    static constexpr bool kTw3Pow = KCT > 5;    // same for pass 3
+    // teams of two at KCT > 4 (168-register budget): both twiddle tables live in shared memory
+    static constexpr bool kTwShared = TEAM == 2 && KCT > 4;
+    static constexpr int kTw2Mode = kTwShared ? kTwSmem : (KCT > 4 ? kTwPow : kTwFull);   // KCT = 5, 6 without teams: keep r, r^2, r^4
+    static constexpr int kTw3Mode = kTwShared ? kTwSmem : (KCT > 5 ? kTwPow : kTwFull);
     static constexpr bool kDbX2 = KCT <= 4;     // double-buffered X2 (fits when only 4 groups share the SM)
     static constexpr int kStages = 3;   // key-ring depth (4 measured no faster)
-    static constexpr bool kAccTmem = KCT > 5;   // MAC accumulators in TMEM (KCT = 6 only; measured slower than KCT = 4)
+    static constexpr bool kAccTmem = !kTwShared && KCT > 5;   // MAC accumulators in TMEM (measured slower than KCT = 4)
     static constexpr int kTmemCols = 256;       // 64 columns per warp, up to 3 warps per TMEM quadrant
     static constexpr int kAccBytes = 2 * kN * 4;
     static constexpr int kX1Bytes = kX1Slots * 16;
     static constexpr int kX2Bytes = kX2Slots * 16;
+    static constexpr int kTwBytes = kTwShared ? (kTw2Len + kTw3Len) * 16 : 0;
     __host__ __device__ static constexpr int group_bytes(int n) {
-        return kAccBytes + kX1Bytes + (kDbX2 ? 2 : 1) * kX2Bytes + align16((n + 1) * 2);
+        int b = kAccBytes + kX1Bytes + (kDbX2 ? 2 : 1) * kX2Bytes + align16((n + 1) * 2);
+        // teams of two: consecutive groups sit 64 (mod 128) bytes apart, i.e. on complementary bank halves
+        while (TEAM == 2 && (b & 127) != 64) b += 16;
+        return b;
     }
 };
 
-template <int KCT, bool USE_TMA, bool MARGIN>
+template <int KCT, bool USE_TMA, bool MARGIN, int TEAM = 1>
 __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(const BrArgs P) {
-    using Lay = Layout<KCT>;
-    constexpr bool POW = Lay::kTw2Pow, POW3 = Lay::kTw3Pow, DBX2 = Lay::kDbX2;
+    using Lay = Layout<KCT, TEAM>;
+    constexpr int POW = Lay::kTw2Mode, POW3 = Lay::kTw3Mode;
+    constexpr bool DBX2 = Lay::kDbX2;
     constexpr int kStages = Lay::kStages;
     constexpr bool ACCT = Lay::kAccTmem;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -223,7 +239,11 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(ptr + 64);
     ptr += 80;
     const int n = P.n, L = P.L, bgbit = P.bgbit;
+    static_assert(TEAM == 1 || (TEAM == 2 && KCT % 2 == 0), "a team never straddles CTAs");
+    constexpr int kTeamThreads = TEAM * kGroupThreads;
     const int group_bytes = Lay::group_bytes(n);
+    cplx *tw_tab = reinterpret_cast<cplx *>(ptr);   // [tw2 | tw3] when the twiddles live in shared memory
+    ptr += Lay::kTwBytes;
 
     const int tid = threadIdx.x;
     const int first_ct = blockIdx.x * KCT;
@@ -232,10 +252,13 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
     if (USE_TMA && tid == 0) {
         for (int s = 0; s < kStages; s++) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], n_active * 2);   // one arrival per consumer warp
+            mbar_init(&empty_bar[s], ((n_active + TEAM - 1) / TEAM) * TEAM * 2);   // one arrival per consumer warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (Lay::kTwShared) {
+        for (int j = tid; j < kTw2Len + kTw3Len; j += KCT * kGroupThreads) tw_tab[j] = j < kTw2Len ? P.tw2[j] : P.tw3[j - kTw2Len];
     }
     if (ACCT && tid < 32) {
         tmem_alloc(tmem_slot, Lay::kTmemCols);
@@ -248,10 +271,22 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
         tmem_base = *tmem_slot;
     }
 
-    const int g = tid >> 6, t = tid & 63;
-    if (g >= n_active) return;   // (warp 0 belongs to group 0, always active: it frees the TMEM allocation at the end)
+    // TEAM = 2: two ciphertexts share each warp in adjacent lanes (lane = 2 j + c).  LDS.128 merges adjacent lane
+    // pairs reading the same 16 bytes (tools/microbench.cu M1), so the key reads of the pointwise MAC -- identical
+    // for both ciphertexts -- cost half the shared-memory wavefronts; the two ciphertexts' buffers differ by 64
+    // (mod 128) bytes, so every quarter-warp phase of the exchanges still covers 8 distinct 16-byte bank groups.
+    int g, t, team;
+    if (TEAM == 1) {
+        g = tid >> 6; t = tid & 63; team = g;
+    } else {
+        team = tid >> 7;
+        t = 16 * ((tid >> 5) & 3) + ((tid & 31) >> 1);
+        g = 2 * team + (tid & 1);
+    }
+    if (team * TEAM >= n_active) return;   // whole warps (warp 0 is always active: it frees the TMEM allocation at the end)
+    const bool live = g < n_active;        // TEAM = 2: the ghost half of a last, odd team mirrors its partner
     const int hi = t >> 3, lo = t & 7;
-    const int barid = 1 + g;
+    const int barid = 1 + team;
     // this warp's TMEM window: lane quadrant (warp & 3), 64 columns per warp sharing that quadrant
     const uint32_t my_tmem = tmem_base + ((uint32_t)((tid >> 5) & 3) << 21) + (uint32_t)(tid >> 7) * 64u;
     unsigned char *gb = ptr + (size_t)g * group_bytes;
@@ -262,18 +297,22 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
     xb.x2 = reinterpret_cast<cplx *>(gb + Lay::kAccBytes + Lay::kX1Bytes);
     xb.flip = 0;
     uint16_t *atil = reinterpret_cast<uint16_t *>(gb + Lay::kAccBytes + Lay::kX1Bytes + (DBX2 ? 2 : 1) * Lay::kX2Bytes);
-    const size_t ct = (size_t)first_ct + g;
+    const size_t ct = (size_t)first_ct + (live ? g : g - 1);
 
-    // per-thread twiddles, register-resident for the whole kernel: role B node q2 = lo, role C node t
+    // per-thread twiddles: role B node q2 = lo, role C node t
     Tw2<POW> tw2;
     Tw2<POW3> tw3;
-    if (POW3) {
+    if (POW3 == kTwSmem) {
+        tw3.tab = tw_tab + kTw2Len + tw3_index(1, t); tw3.stride = 64;
+    } else if (POW3 == kTwPow) {
         tw3.w[0] = P.tw3[tw3_index(1, t)]; tw3.w[1] = P.tw3[tw3_index(2, t)]; tw3.w[2] = P.tw3[tw3_index(4, t)];
     } else {
 #pragma unroll
         for (int p = 1; p < 8; p++) tw3.w[p - 1] = P.tw3[tw3_index(p, t)];
     }
-    if (POW) {
+    if (POW == kTwSmem) {
+        tw2.tab = tw_tab + tw2_index(1, lo); tw2.stride = 8;
+    } else if (POW == kTwPow) {
         tw2.w[0] = P.tw2[tw2_index(1, lo)]; tw2.w[1] = P.tw2[tw2_index(2, lo)]; tw2.w[2] = P.tw2[tw2_index(4, lo)];
     } else {
 #pragma unroll
@@ -292,7 +331,7 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
             atil[i] = (uint16_t)((i == n) ? (2 * kN - m) : m);
         }
     }
-    bar_sync(barid, kGroupThreads);
+    bar_sync(barid, kTeamThreads);
     // ---- acc = X^btil * testvec (trgsw.zig:300-306), stored in acc_pos order
     {
         const int btil = atil[n];
@@ -305,7 +344,7 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
             acc_b[acc_pos(j)] = (u & kN) ? 0u - vb : vb;
         }
     }
-    bar_sync(barid, kGroupThreads);
+    bar_sync(barid, kTeamThreads);
 
     const uint32_t mask = (1u << bgbit) - 1u, half_bg = 1u << (bgbit - 1);
     const uint32_t offset = P.offset;
@@ -340,7 +379,7 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
                 for (int l = 0; l < L; l++) {
                     cplx v[8];
                     digits_to_cplx(v, d, 32 - (l + 1) * bgbit, mask, half_bg);
-                    fwd_transform<USE_TMA, DBX2, POW, POW3>(v, xb, tw2, tw3, hi, lo, barid, pr);
+                    fwd_transform<USE_TMA, DBX2, POW, POW3>(v, xb, tw2, tw3, hi, lo, barid, pr, kTeamThreads);
                     const cplx *chunk;
                     if (USE_TMA) {
                         while (!mbar_try_wait(&full_bar[stage], phase)) producer_poll(pr);
@@ -355,14 +394,14 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
                     }
                     if (USE_TMA) {
                         __syncwarp();
-                        if ((t & 31) == 0) mbar_arrive(&empty_bar[stage]);
+                        if ((tid & 31) == 0) mbar_arrive(&empty_bar[stage]);
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
-            inv_transform<USE_TMA, DBX2, POW, POW3>(oa, xb, tw2, tw3, hi, lo, barid, pr);
+            inv_transform<USE_TMA, DBX2, POW, POW3>(oa, xb, tw2, tw3, hi, lo, barid, pr, kTeamThreads);
             round_accumulate<MARGIN>(oa, acc_a, t, wide, margin);
-            inv_transform<USE_TMA, DBX2, POW, POW3>(ob, xb, tw2, tw3, hi, lo, barid, pr);
+            inv_transform<USE_TMA, DBX2, POW, POW3>(ob, xb, tw2, tw3, hi, lo, barid, pr, kTeamThreads);
             round_accumulate<MARGIN>(ob, acc_b, t, wide, margin);
         } else {
             // ---- accumulators in TMEM (168-register budget): each half is loaded, updated and stored back
@@ -375,7 +414,7 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
                 for (int l = 0; l < L; l++) {
                     cplx v[8];
                     digits_to_cplx(v, d, 32 - (l + 1) * bgbit, mask, half_bg);
-                    fwd_transform<USE_TMA, DBX2, POW, POW3>(v, xb, tw2, tw3, hi, lo, barid, pr);
+                    fwd_transform<USE_TMA, DBX2, POW, POW3>(v, xb, tw2, tw3, hi, lo, barid, pr, kTeamThreads);
                     const cplx *chunk;
                     if (USE_TMA) {
                         while (!mbar_try_wait(&full_bar[stage], phase)) producer_poll(pr);
@@ -399,7 +438,7 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
                     }
                     if (USE_TMA) {
                         __syncwarp();
-                        if ((t & 31) == 0) mbar_arrive(&empty_bar[stage]);
+                        if ((tid & 31) == 0) mbar_arrive(&empty_bar[stage]);
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -408,19 +447,19 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
             for (int ab = 0; ab < 2; ab++) {
                 cplx o[8];
                 tmem_load_cplx8(o, my_tmem + 32 * ab);
-                inv_transform<USE_TMA, DBX2, POW, POW3>(o, xb, tw2, tw3, hi, lo, barid, pr);
+                inv_transform<USE_TMA, DBX2, POW, POW3>(o, xb, tw2, tw3, hi, lo, barid, pr, kTeamThreads);
                 round_accumulate<MARGIN>(o, ab ? acc_b : acc_a, t, wide, margin);
             }
         }
-        bar_sync(barid, kGroupThreads);   // accumulator complete before the next rotated reads
+        bar_sync(barid, kTeamThreads);   // accumulator complete before the next rotated reads
     }
 
     // ---- epilogue
-    if (P.out_trlwe) {
+    if (live && P.out_trlwe) {
         uint32_t *o = P.out_trlwe + ct * (size_t)(2 * kN);
         for (int j = t; j < kN; j += kGroupThreads) { o[j] = acc_a[acc_pos(j)]; o[kN + j] = acc_b[acc_pos(j)]; }
     }
-    if (P.out_lv1) {   // sampleExtractIndex(., 0): trlwe.zig:146-162
+    if (live && P.out_lv1) {   // sampleExtractIndex(., 0): trlwe.zig:146-162
         uint32_t *o = P.out_lv1 + ct * (size_t)(kN + 1);
         for (int j = t; j <= kN; j += kGroupThreads)
             o[j] = (j == 0) ? acc_a[0] : (j == kN) ? acc_b[0] : 0u - acc_a[acc_pos(kN - j)];
@@ -428,12 +467,12 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
     if (MARGIN && P.margin_bits) {
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) margin = fmax(margin, __shfl_xor_sync(0xffffffffu, margin, s));
-        if ((t & 31) == 0) atomicMax(P.margin_bits, (unsigned long long)__double_as_longlong(margin));
+        if ((tid & 31) == 0) atomicMax(P.margin_bits, (unsigned long long)__double_as_longlong(margin));
     }
     if (ACCT) {
         tmem_wait_st();
         tmem_fence_before_sync();
-        bar_sync(15, n_active * kGroupThreads);      // every active warp is done with its TMEM window
+        bar_sync(15, ((n_active + TEAM - 1) / TEAM) * kTeamThreads);      // every active warp is done with its TMEM window
         if (tid < 32) {
             tmem_fence_after_sync();
             tmem_dealloc(tmem_base, Lay::kTmemCols);
@@ -452,7 +491,7 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
 template <int L, bool MARGIN>
 __global__ void __launch_bounds__(2 * L * kGroupThreads, 1) blind_rotate_latency_kernel(const BrArgs P) {
     constexpr int G = 2 * L;
-    constexpr bool POW = (L >= 3);    // 384 threads -> 168 registers: expand twiddle powers per pass
+    constexpr int POW = (L >= 3) ? kTwPow : kTwFull;    // 384 threads -> 168 registers: expand twiddle powers per pass
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t *acc_a = reinterpret_cast<uint32_t *>(smem_raw), *acc_b = acc_a + kN;
     cplx *red = reinterpret_cast<cplx *>(smem_raw + 2 * kN * 4);                      // [G][ab][q][t]
@@ -481,7 +520,7 @@ __global__ void __launch_bounds__(2 * L * kGroupThreads, 1) blind_rotate_latency
     xb.flip = 0;
     Tw2<POW> tw2;
     Tw2<POW> tw3;
-    if (POW) {
+    if (POW == kTwPow) {
         tw2.w[0] = P.tw2[tw2_index(1, lo)]; tw2.w[1] = P.tw2[tw2_index(2, lo)]; tw2.w[2] = P.tw2[tw2_index(4, lo)];
         tw3.w[0] = P.tw3[tw3_index(1, t)]; tw3.w[1] = P.tw3[tw3_index(2, t)]; tw3.w[2] = P.tw3[tw3_index(4, t)];
     } else {
@@ -573,6 +612,312 @@ __global__ void __launch_bounds__(2 * L * kGroupThreads, 1) blind_rotate_latency
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// K1 v3: software-pipelined throughput kernel.  Same arithmetic, layouts and key ring as blind_rotate_kernel
+// (bit-identical results); what changes is the order in which a warp issues its work, and who shares a warp.
+//
+//  * Split exchange barriers.  The cross-warp exchange X2 is guarded by mbarriers that a warp *arrives* on right
+//    after its stores and *waits* on only when it needs the partner's data.  In between it runs pass 1 of the
+//    NEXT digit transform (its registers are free: the current transform's data is in flight through shared
+//    memory), and the quarter-warp exchange X1 of that next transform is in turn covered by pass 3 + the
+//    pointwise MAC of the current one.  The two inverse transforms of an iteration are interleaved the same
+//    way, and the end-of-iteration barrier is split per accumulator half (a, b).  No extra registers: a
+//    transform whose data sits in an exchange buffer owns no registers.
+//  * Teams (TEAM = 2).  Two ciphertexts share each warp in adjacent lanes (lane = 2 j + c).  LDS.128 merges
+//    adjacent lane pairs that read the same 16 bytes (measured on B200, tools/microbench.cu M1 pattern 3: 2.0
+//    instead of 4.0 cycles per instruction), so the bootstrapping-key reads of the pointwise MAC -- identical
+//    for every ciphertext -- cost half the shared-memory wavefronts.  The two ciphertexts' buffers sit at
+//    offsets that differ by 64 (mod 128) bytes, which keeps every quarter-warp phase of the exchange
+//    stores/loads on 8 distinct 16-byte bank groups.
+struct TeamSync {
+    uint64_t *x2;      // [2]: one mbarrier per X2 buffer
+    uint64_t *acc_a;   // accumulator half a complete (round_accumulate of every team warp done)
+    uint64_t *acc_b;
+};
+
+// The producer's warp must never sit in a suspended try_wait: the warp it waits for may itself be waiting for a
+// key chunk only the producer can issue.  It spins on the non-blocking test_wait and keeps polling the ring.
+template <bool PRODUCER>
+__device__ __forceinline__ void team_wait(uint64_t *bar, uint32_t parity, Producer &pr, bool prod_warp) {
+    if (PRODUCER && prod_warp) {
+        while (!mbar_test_wait(bar, parity)) producer_poll(pr);
+    } else {
+        while (!mbar_try_wait(bar, parity)) {
+        }
+    }
+}
+__device__ __forceinline__ void team_signal(uint64_t *bar, int lane) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+}
+
+__host__ __device__ constexpr int swp_group_bytes(int n) {
+    // accumulator + X1 + two X2 buffers + modulus-switched mask; padded to 64 (mod 128) so that the two
+    // ciphertexts of a team occupy complementary bank halves
+    int b = 2 * kN * 4 + kX1Slots * 16 + 2 * kX2Slots * 16 + align16((n + 1) * 2);
+    while ((b & 127) != 64) b += 16;
+    return b;
+}
+constexpr int kSwpStages = 3;
+constexpr int kSwpHeaderBytes = 64 + 4 * 4 * 8;   // key-ring barriers + up to 4 teams x 4 mbarriers
+
+template <int KCT, int TEAM, bool MARGIN>
+__global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_swp_kernel(const BrArgs P) {
+    static_assert(KCT % TEAM == 0, "a team never straddles CTAs");
+    constexpr int kTeamWarps = 2 * TEAM;
+    constexpr int kTeamThreads = TEAM * kGroupThreads;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cplx *bsk_ring = reinterpret_cast<cplx *>(smem_raw);
+    unsigned char *ptr = smem_raw + kSwpStages * kBskChunkBytes;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(ptr);
+    uint64_t *empty_bar = full_bar + 4;
+    uint64_t *team_bars = full_bar + 8;
+    ptr += kSwpHeaderBytes;
+    const int n = P.n, L = P.L, bgbit = P.bgbit;
+    const int group_bytes = swp_group_bytes(n);
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int first_ct = blockIdx.x * KCT;
+    const int n_active = min(KCT, (int)P.B - first_ct);
+    const int active_teams = (n_active + TEAM - 1) / TEAM;
+
+    if (tid == 0) {
+        for (int s = 0; s < kSwpStages; s++) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], active_teams * kTeamWarps);   // one arrival per consumer warp
+        }
+        for (int b = 0; b < 4 * active_teams; b++) mbar_init(&team_bars[b], kTeamWarps);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    int team, g, t;
+    if (TEAM == 1) {
+        g = tid >> 6; t = tid & 63; team = g;
+    } else {
+        team = tid >> 7;
+        t = 16 * ((tid >> 5) & 3) + (lane >> 1);
+        g = 2 * team + (lane & 1);
+    }
+    if (team >= active_teams) return;            // whole warps
+    const bool live = g < n_active;              // TEAM = 2: the ghost half of a last, odd team mirrors its partner
+    const size_t ct = (size_t)first_ct + (live ? g : g - 1);
+    const int hi = t >> 3, lo = t & 7;
+    TeamSync ts;
+    ts.x2 = team_bars + 4 * team; ts.acc_a = ts.x2 + 2; ts.acc_b = ts.x2 + 3;
+    const int team_barid = 1 + team;
+
+    unsigned char *gb = ptr + (size_t)g * group_bytes;
+    uint32_t *acc_a = reinterpret_cast<uint32_t *>(gb);
+    uint32_t *acc_b = acc_a + kN;
+    cplx *x1 = reinterpret_cast<cplx *>(gb + 2 * kN * 4);
+    cplx *x2base = x1 + kX1Slots;
+    uint16_t *atil = reinterpret_cast<uint16_t *>(gb + 2 * kN * 4 + kX1Slots * 16 + 2 * kX2Slots * 16);
+
+    Tw2<kTwFull> tw2, tw3;
+#pragma unroll
+    for (int p = 1; p < 8; p++) { tw3.w[p - 1] = P.tw3[tw3_index(p, t)]; tw2.w[p - 1] = P.tw2[tw2_index(p, lo)]; }
+
+    // ---- prologue: gate linear part (gates.zig:48-121) + modulus switch (trgsw.zig:297,312)
+    {
+        const int op = P.ops ? P.ops[ct] : P.op;
+        const uint32_t *ia = P.in_a + ct * (size_t)(n + 1);
+        const uint32_t *ib = (op >= 0) ? P.in_b + ct * (size_t)(n + 1) : ia;
+        for (int i = t; i <= n; i += kGroupThreads) {
+            uint32_t lin = gate_linear(op, ia[i], ib[i]);
+            if (i == n) lin += gate_constant(op);
+            const uint32_t m = (uint32_t)(((unsigned long long)lin + (1u << 20)) >> 21);   // in [0, 2N]
+            atil[i] = (uint16_t)((i == n) ? (2 * kN - m) : m);
+        }
+    }
+    bar_sync(team_barid, kTeamThreads);
+    {   // acc = X^btil * testvec (trgsw.zig:300-306), stored in acc_pos order
+        const int btil = atil[n];
+        const uint32_t *tv = P.testvec ? P.testvec + (P.tv_per_item ? ct * (size_t)(2 * kN) : 0) : nullptr;
+        for (int j = t; j < kN; j += kGroupThreads) {
+            const int u = (j - btil) & (2 * kN - 1);
+            const uint32_t va = tv ? tv[u & (kN - 1)] : 0u;
+            const uint32_t vb = tv ? tv[kN + (u & (kN - 1))] : 0x20000000u;   // key.zig:134-145
+            acc_a[acc_pos(j)] = (u & kN) ? 0u - va : va;
+            acc_b[acc_pos(j)] = (u & kN) ? 0u - vb : vb;
+        }
+    }
+    bar_sync(team_barid, kTeamThreads);
+
+    const uint32_t mask = (1u << bgbit) - 1u, half_bg = 1u << (bgbit - 1);
+    const uint32_t offset = P.offset;
+    const int wide = P.wide_round;
+    const int twoL = 2 * L;
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t xk = 0;              // X2 exchange counter: buffer xk & 1, barrier phase parity (xk >> 1) & 1
+    double margin = 0.0;
+    Producer pr;
+    pr.src = P.bsk; pr.ring = bsk_ring; pr.full_bar = full_bar; pr.empty_bar = empty_bar;
+    pr.remaining = n * twoL; pr.issued = 0; pr.stage = 0; pr.phase = 0; pr.stages = kSwpStages;
+    pr.active = tid == 0;
+    const bool prod_warp = tid < 32;
+    pr.policy = pr.active ? l2_policy_evict_last() : 0;
+#pragma unroll
+    for (int s = 0; s < kSwpStages; s++) producer_poll(pr);
+
+    // ---- n CMUX steps (trgsw.zig:311-330)
+    for (int i = 0; i < n; i++) {
+        const int at = atil[i];
+        const uint32_t prev = (uint32_t)(i - 1) & 1u;
+        cplx oa[8], ob[8], v[8];
+        uint32_t d[16];
+#pragma unroll
+        for (int q = 0; q < 8; q++) { oa[q] = cplx{0.0, 0.0}; ob[q] = cplx{0.0, 0.0}; }
+        if (i > 0) team_wait<true>(ts.acc_a, prev, pr, prod_warp);      // every team warp has added its part of acc_a
+        load_rot_diffs(d, acc_a, at, offset, hi, lo);
+        // stage A of transform 0: digits -> pass 1 -> X1
+        digits_to_cplx(v, d, 32 - bgbit, mask, half_bg);
+        fwd_pass1(v);
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 8; q++) x1[x1_slot(hi, q, lo)] = v[q];
+#pragma unroll 1
+        for (int k = 0; k < twoL; k++) {
+            // ---- stage B(k): X1 -> pass 2 -> X2, arrive
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 8; q++) v[q] = x1[x1_slot(hi, lo, q)];
+            fwd_pass(v, tw2.w, 1);
+            producer_poll(pr);
+            {
+                cplx *x2 = x2base + (xk & 1u) * kX2Slots;
+#pragma unroll
+                for (int q = 0; q < 8; q++) x2[x2_slot(lo, q, hi)] = v[q];
+            }
+            team_signal(&ts.x2[xk & 1u], lane);
+            // ---- stage A(k+1): the next transform's pass 1 runs while X2 of transform k is in flight
+            if (k + 1 < twoL) {
+                int l1 = k + 1;
+                if (l1 >= L) l1 -= L;
+                if (k + 1 == L) {      // digits of the b polynomial (trgsw.zig:211-217)
+                    if (i > 0) team_wait<true>(ts.acc_b, prev, pr, prod_warp);
+                    load_rot_diffs(d, acc_b, at, offset, hi, lo);
+                }
+                digits_to_cplx(v, d, 32 - (l1 + 1) * bgbit, mask, half_bg);
+                fwd_pass1(v);
+                __syncwarp();          // every lane of the quarter-warp has read X1 of transform k
+#pragma unroll
+                for (int q = 0; q < 8; q++) x1[x1_slot(hi, q, lo)] = v[q];
+            }
+            // ---- stage C(k): X2 -> pass 3 -> pointwise MAC with key chunk (i, k)
+            team_wait<true>(&ts.x2[xk & 1u], (xk >> 1) & 1u, pr, prod_warp);
+            {
+                const cplx *x2 = x2base + (xk & 1u) * kX2Slots;
+#pragma unroll
+                for (int q = 0; q < 8; q++) v[q] = x2[x2_slot(hi, lo, q)];
+            }
+            xk++;
+            fwd_pass(v, tw3.w, 1);
+            team_wait<true>(&full_bar[stage], phase, pr, prod_warp);
+            {
+                const cplx *chunk = bsk_ring + stage * kBskChunkCplx;
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    cmac(oa[q], v[q], chunk[bsk_slot(0, q, t)]);
+                    cmac(ob[q], v[q], chunk[bsk_slot(1, q, t)]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[stage]);
+            producer_poll(pr);
+            if (++stage == kSwpStages) { stage = 0; phase ^= 1; }
+        }
+        // ---- the two inverse transforms, interleaved
+        const uint32_t ka = xk, kb = xk + 1;
+        xk += 2;
+        inv_pass(oa, tw3.w, 1);
+        {
+            cplx *x2 = x2base + (ka & 1u) * kX2Slots;
+#pragma unroll
+            for (int q = 0; q < 8; q++) x2[x2_slot(hi, lo, q)] = oa[q];
+        }
+        team_signal(&ts.x2[ka & 1u], lane);
+        inv_pass(ob, tw3.w, 1);
+        producer_poll(pr);
+        // every reader of the other X2 buffer (last forward transform) has arrived on exchange ka
+        team_wait<true>(&ts.x2[ka & 1u], (ka >> 1) & 1u, pr, prod_warp);
+        {
+            cplx *x2 = x2base + (kb & 1u) * kX2Slots;
+#pragma unroll
+            for (int q = 0; q < 8; q++) x2[x2_slot(hi, lo, q)] = ob[q];
+        }
+        team_signal(&ts.x2[kb & 1u], lane);
+        {
+            const cplx *x2 = x2base + (ka & 1u) * kX2Slots;
+#pragma unroll
+            for (int q = 0; q < 8; q++) oa[q] = x2[x2_slot(lo, q, hi)];
+        }
+        inv_pass(oa, tw2.w, 1);
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 8; q++) x1[x1_slot(hi, lo, q)] = oa[q];
+        team_wait<true>(&ts.x2[kb & 1u], (kb >> 1) & 1u, pr, prod_warp);
+        {
+            const cplx *x2 = x2base + (kb & 1u) * kX2Slots;
+#pragma unroll
+            for (int q = 0; q < 8; q++) ob[q] = x2[x2_slot(lo, q, hi)];
+        }
+        inv_pass(ob, tw2.w, 1);
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 8; q++) oa[q] = x1[x1_slot(hi, q, lo)];
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 8; q++) x1[x1_slot(hi, lo, q)] = ob[q];
+        inv_pass1(oa);
+        round_accumulate<MARGIN>(oa, acc_a, t, wide, margin);
+        team_signal(ts.acc_a, lane);
+#pragma unroll
+        for (int q = 0; q < 8; q++) ob[q] = x1[x1_slot(hi, q, lo)];
+        inv_pass1(ob);
+        round_accumulate<MARGIN>(ob, acc_b, t, wide, margin);
+        team_signal(ts.acc_b, lane);
+    }
+    {
+        const uint32_t last = (uint32_t)(n - 1) & 1u;
+        team_wait<false>(ts.acc_a, last, pr, false);
+        team_wait<false>(ts.acc_b, last, pr, false);
+    }
+
+    // ---- epilogue
+    if (live && P.out_trlwe) {
+        uint32_t *o = P.out_trlwe + ct * (size_t)(2 * kN);
+        for (int j = t; j < kN; j += kGroupThreads) { o[j] = acc_a[acc_pos(j)]; o[kN + j] = acc_b[acc_pos(j)]; }
+    }
+    if (live && P.out_lv1) {   // sampleExtractIndex(., 0): trlwe.zig:146-162
+        uint32_t *o = P.out_lv1 + ct * (size_t)(kN + 1);
+        for (int j = t; j <= kN; j += kGroupThreads)
+            o[j] = (j == 0) ? acc_a[0] : (j == kN) ? acc_b[0] : 0u - acc_a[acc_pos(kN - j)];
+    }
+    if (MARGIN && P.margin_bits) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) margin = fmax(margin, __shfl_xor_sync(0xffffffffu, margin, s));
+        if (lane == 0) atomicMax(P.margin_bits, (unsigned long long)__double_as_longlong(margin));
+    }
+}
+
+template <int KCT, int TEAM, bool MARGIN>
+cudaError_t launch_swp_variant(const BrArgs &a, cudaStream_t s) {
+    const size_t smem = kSwpStages * kBskChunkBytes + kSwpHeaderBytes + (size_t)KCT * swp_group_bytes(a.n);
+    auto kern = blind_rotate_swp_kernel<KCT, TEAM, MARGIN>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const unsigned grid = (a.B + KCT - 1) / KCT;
+    kern<<<grid, KCT * kGroupThreads, smem, s>>>(a);
+    return cudaGetLastError();
+}
+template <int KCT, int TEAM>
+cudaError_t launch_swp(const BrArgs &a, bool margin, cudaStream_t s) {
+    return margin ? launch_swp_variant<KCT, TEAM, true>(a, s) : launch_swp_variant<KCT, TEAM, false>(a, s);
+}
+
 template <int L, bool MARGIN>
 cudaError_t launch_latency(const BrArgs &a, cudaStream_t s) {
     constexpr int G = 2 * L;
@@ -584,17 +929,22 @@ cudaError_t launch_latency(const BrArgs &a, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-template <int KCT, bool USE_TMA, bool MARGIN>
+template <int KCT, bool USE_TMA, bool MARGIN, int TEAM = 1>
 cudaError_t launch_variant(const BrArgs &a, cudaStream_t s) {
-    using Lay = Layout<KCT>;
+    using Lay = Layout<KCT, TEAM>;
     const int threads = KCT * kGroupThreads;
-    const size_t smem = (USE_TMA ? Lay::kStages * kBskChunkBytes : 0) + 80 + (size_t)KCT * Lay::group_bytes(a.n);
-    auto kern = blind_rotate_kernel<KCT, USE_TMA, MARGIN>;
+    const size_t smem = (USE_TMA ? Lay::kStages * kBskChunkBytes : 0) + 80 + Lay::kTwBytes + (size_t)KCT * Lay::group_bytes(a.n);
+    auto kern = blind_rotate_kernel<KCT, USE_TMA, MARGIN, TEAM>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const unsigned grid = (a.B + KCT - 1) / KCT;
     kern<<<grid, threads, smem, s>>>(a);
     return cudaGetLastError();
+}
+
+template <int KCT>
+cudaError_t launch_team2(const BrArgs &a, bool margin, cudaStream_t s) {
+    return margin ? launch_variant<KCT, true, true, 2>(a, s) : launch_variant<KCT, true, false, 2>(a, s);
 }
 
 template <int KCT>
@@ -621,17 +971,30 @@ cudaError_t launch_blind_rotate(const BrArgs &a, const BrTuning &tune, bool trac
     int kct = tune.kct;
     if (kct <= 0) {
         // minimise (number of CTA waves) x (time of one CTA at that width); CTA times measured on B200 at n = 700
-        // (profiles/r01_first_light*.log): 1 or 2 ciphertexts 4.5 ms, 3: 6.1 ms, 4: 6.5 ms
-        static const double t_cta[5] = {0.0, 4.5, 4.5, 6.1, 6.46};
+        // (profiles/r01_first_light*.log, profiles/r01_team_probe.log): 1 or 2 ciphertexts 4.5 ms, 3: 6.1 ms, 4: 6.5 ms,
+        // 6 (teams of two, shared-memory twiddles): 7.9 ms
+        static const double t_cta[7] = {0.0, 4.5, 4.5, 6.1, 6.5, 1e9, 7.9};
+        const bool team2 = tune.team != 1;
         const unsigned sms = tune.sm_count > 0 ? (unsigned)tune.sm_count : 148u;
         double best = 1e30;
-        for (int k = 1; k <= 4; k++) {
+        for (int k = 1; k <= (team2 && tune.use_tma != 0 ? 6 : 4); k++) {
             const unsigned waves = (a.B + sms * k - 1) / (sms * k);
             const double cost = waves * t_cta[k];
             if (cost < best - 1e-9) { best = cost; kct = k; }
         }
     }
     if (launches) (*launches)++;
+    if (tune.pipeline != 0 && tune.use_tma != 0 && kct <= 4) {
+        const bool team2 = tune.team == 2;
+        switch (kct) {
+            case 1: return launch_swp<1, 1>(a, track_margin, s);
+            case 2: return team2 ? launch_swp<2, 2>(a, track_margin, s) : launch_swp<2, 1>(a, track_margin, s);
+            case 3: return launch_swp<3, 1>(a, track_margin, s);
+            default: return team2 ? launch_swp<4, 2>(a, track_margin, s) : launch_swp<4, 1>(a, track_margin, s);
+        }
+    }
+    if (tune.use_tma != 0 && ((kct == 6 && tune.team != 1) || ((kct == 2 || kct == 4) && tune.team == 2)))
+        return kct == 2 ? launch_team2<2>(a, track_margin, s) : kct == 4 ? launch_team2<4>(a, track_margin, s) : launch_team2<6>(a, track_margin, s);
     switch (kct) {
         case 1: return launch_kct<1>(a, tune.use_tma != 0, track_margin, s);
         case 2: return launch_kct<2>(a, tune.use_tma != 0, track_margin, s);

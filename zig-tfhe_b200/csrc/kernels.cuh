@@ -32,6 +32,8 @@ struct BrTuning {
     int use_tma = 1;    // stream key chunks with cp.async.bulk + mbarrier (0: direct global loads)
     int sm_count = 0;   // SMs of the target device (wave-quantisation aware choice of kct)
     int latency_mode = 1;   // batches <= sm_count: one CTA per ciphertext, transforms of an iteration in parallel
+    int pipeline = 0;   // 1: software-pipelined variant (split mbarrier exchanges; measured slower, kept for A/B), 0: bar.sync kernel
+    int team = 0;       // ciphertexts sharing a warp in adjacent lanes (0 = default, 1, 2)
 };
 
 // returns cudaSuccess or the launch error; *launches += kernels launched
