@@ -67,7 +67,7 @@ def main():
     stage(f"pipelined == round-1 kernel on B={big}", cross)
 
     ctx.set_tuning("timing", 1)
-    nb = 148 * 4 * 4
+    nb = 148 * 6 * 4
     A = np.tile(ca, (nb // 64 + 1, 1))[:nb]; Bm = np.tile(cb, (nb // 64 + 1, 1))[:nb]
     for (pipe, team, kct) in [(0, 1, 4), (0, 2, 4), (0, 2, 6), (0, 1, 6)]:
         def run(pipe=pipe, team=team, kct=kct):

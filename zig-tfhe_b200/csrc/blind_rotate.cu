@@ -35,8 +35,9 @@ namespace tfhe_b200 {
 
 namespace {
 
-// Teams of two pay off where they free registers (KCT = 6: 112.9 k vs 90.8 k bootstraps/s at KCT = 4); at KCT <= 4 the
-// wider barriers cost 2 % (measured, profiles/r01_team_probe.log), so the default keeps one ciphertext per warp pair there.
+// Teams of two (tuning key "team") cut the shared-memory wavefronts by 11 % (ncu) but the kernel is latency-bound,
+// not shared-memory-bound: 88.8 k vs 90.8 k bootstraps/s at KCT = 4, 83.9 k at KCT = 6 with shared-memory twiddles
+// (profiles/r01_team_probe.log, r01_wave_scaling.log).  The default stays one ciphertext per warp pair, KCT = 4.
 constexpr int kMaxStages = 4;  // deepest key ring (16 KiB per stage); Layout<KCT>::kStages picks the depth
 
 // Key-ring producer state, live only in thread 0 of the CTA (see header comment).
@@ -971,13 +972,12 @@ cudaError_t launch_blind_rotate(const BrArgs &a, const BrTuning &tune, bool trac
     int kct = tune.kct;
     if (kct <= 0) {
         // minimise (number of CTA waves) x (time of one CTA at that width); CTA times measured on B200 at n = 700
-        // (profiles/r01_first_light*.log, profiles/r01_team_probe.log): 1 or 2 ciphertexts 4.5 ms, 3: 6.1 ms, 4: 6.5 ms,
-        // 6 (teams of two, shared-memory twiddles): 7.9 ms
-        static const double t_cta[7] = {0.0, 4.5, 4.5, 6.1, 6.5, 1e9, 7.9};
-        const bool team2 = tune.team != 1;
+        // (profiles/r01_first_light*.log, profiles/r01_wave_scaling.log): 1 or 2 ciphertexts 4.5 ms, 3: 6.1 ms, 4: 6.5 ms.
+        // (6 with teams of two and shared-memory twiddles: 10.6 ms -- 84 k/s against 91 k/s at 4, so never chosen.)
+        static const double t_cta[5] = {0.0, 4.5, 4.5, 6.1, 6.5};
         const unsigned sms = tune.sm_count > 0 ? (unsigned)tune.sm_count : 148u;
         double best = 1e30;
-        for (int k = 1; k <= (team2 && tune.use_tma != 0 ? 6 : 4); k++) {
+        for (int k = 1; k <= 4; k++) {
             const unsigned waves = (a.B + sms * k - 1) / (sms * k);
             const double cost = waves * t_cta[k];
             if (cost < best - 1e-9) { best = cost; kct = k; }
@@ -993,7 +993,7 @@ cudaError_t launch_blind_rotate(const BrArgs &a, const BrTuning &tune, bool trac
             default: return team2 ? launch_swp<4, 2>(a, track_margin, s) : launch_swp<4, 1>(a, track_margin, s);
         }
     }
-    if (tune.use_tma != 0 && ((kct == 6 && tune.team != 1) || ((kct == 2 || kct == 4) && tune.team == 2)))
+    if (tune.use_tma != 0 && (kct == 2 || kct == 4 || kct == 6) && tune.team == 2)
         return kct == 2 ? launch_team2<2>(a, track_margin, s) : kct == 4 ? launch_team2<4>(a, track_margin, s) : launch_team2<6>(a, track_margin, s);
     switch (kct) {
         case 1: return launch_kct<1>(a, tune.use_tma != 0, track_margin, s);
