@@ -158,6 +158,64 @@ __global__ void __launch_bounds__(512, 1) tmem_kernel(unsigned long long *cycles
     }
 }
 
+static double avg_cycles(unsigned long long *d, int n);
+
+// ---------------------------------------------------------------- M4: STS.128 and mixed STS/LDS throughput
+// MODE 0: 4 x STS.128; 1: 2 x STS.128 + 2 x LDS.128; 2: 4 x LDS.128 + 8 dependent-free DFMA per lane (pipe overlap)
+template <int MODE>
+__global__ void __launch_bounds__(1024, 1) sts128_kernel(unsigned long long *cycles, uint32_t *sink, int iters) {
+    extern __shared__ __align__(128) unsigned char sm[];
+    for (int i = threadIdx.x; i < 32768 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(sm)[i] = i;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t base = smem_u32(sm) + lane * 16 + ((threadIdx.x >> 5) & 3) * 2048;
+    uint32_t s0 = threadIdx.x, s1 = 1, s2 = 2, s3 = 3;
+    double f0 = 1.0, f1 = 1.1, f2 = 1.2, f3 = 1.3, f4 = 1.4, f5 = 1.5, f6 = 1.6, f7 = 1.7;
+    const double m = 1.0000001, c = 1e-9;
+    const unsigned long long t0 = clock64();
+    for (int it = 0; it < iters; it++) {
+        const uint32_t ad = base + ((it & 7) << 11);
+        if (MODE == 0 || MODE == 1) {
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ad), "r"(s0), "r"(s1), "r"(s2), "r"(s3));
+            asm volatile("st.shared.v4.u32 [%0+512], {%1,%2,%3,%4};" ::"r"(ad), "r"(s1), "r"(s2), "r"(s3), "r"(s0));
+        }
+        if (MODE == 0) {
+            asm volatile("st.shared.v4.u32 [%0+1024], {%1,%2,%3,%4};" ::"r"(ad), "r"(s2), "r"(s3), "r"(s0), "r"(s1));
+            asm volatile("st.shared.v4.u32 [%0+1536], {%1,%2,%3,%4};" ::"r"(ad), "r"(s3), "r"(s0), "r"(s1), "r"(s2));
+        }
+        if (MODE == 1 || MODE == 2) {
+            uint32_t a0, b0, c0, d0, a1, b1, c1, d1;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+1024];" : "=r"(a0), "=r"(b0), "=r"(c0), "=r"(d0) : "r"(ad));
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+1536];" : "=r"(a1), "=r"(b1), "=r"(c1), "=r"(d1) : "r"(ad));
+            s0 += a0 + b0; s1 += c0 + d0; s2 += a1 + b1; s3 += c1 + d1;
+        }
+        if (MODE == 2) {
+            uint32_t a0, b0, c0, d0, a1, b1, c1, d1;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a0), "=r"(b0), "=r"(c0), "=r"(d0) : "r"(ad));
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+512];" : "=r"(a1), "=r"(b1), "=r"(c1), "=r"(d1) : "r"(ad));
+            s0 += a0 + b0; s1 += c0 + d0; s2 += a1 + b1; s3 += c1 + d1;
+            f0 = fma(f0, m, c); f1 = fma(f1, m, c); f2 = fma(f2, m, c); f3 = fma(f3, m, c);
+            f4 = fma(f4, m, c); f5 = fma(f5, m, c); f6 = fma(f6, m, c); f7 = fma(f7, m, c);
+        }
+    }
+    const unsigned long long t1 = clock64();
+    __syncthreads();
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+    if ((s0 ^ s1 ^ s2 ^ s3) == 0x12345678u || f0 + f1 + f2 + f3 + f4 + f5 + f6 + f7 == 3.0) sink[0] = s0;
+}
+template <int MODE>
+static int run_sts(unsigned long long *cyc, uint32_t *sink, const char *what) {
+    const int iters = 4096;
+    CK(cudaFuncSetAttribute(sts128_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768));
+    for (int warps = 8; warps <= 32; warps *= 2) {
+        sts128_kernel<MODE><<<148, warps * 32, 32768>>>(cyc, sink, iters);
+        CK(cudaDeviceSynchronize());
+        const double c = avg_cycles(cyc, 148);
+        printf("M4 %s, %2d warps: %.2f cycles per warp-level 128-bit shared access per SM\n", what, warps, c / (iters * 4.0 * warps));
+    }
+    return 0;
+}
+
 static double avg_cycles(unsigned long long *d, int n) {
     unsigned long long h[1024];
     cudaMemcpy(h, d, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
@@ -216,6 +274,9 @@ int main() {
         CK(cudaDeviceSynchronize());
         printf("M3 SHFL: %.2f cycles per warp-level SHFL per SM (8 warps)\n", avg_cycles(cyc, 148) / (iters * 8.0 * 8.0));
     }
+    if (run_sts<0>(cyc, sink, "4 x STS.128")) return 1;
+    if (run_sts<1>(cyc, sink, "2 x STS.128 + 2 x LDS.128")) return 1;
+    if (run_sts<2>(cyc, sink, "4 x LDS.128 + 8 DFMA")) return 1;
     for (int warps = 4; warps <= 16; warps *= 2) {
         if (run_tmem<0>(cyc, sink, warps, "ld 2 x (32x32b.x32) + wait")) return 1;
         if (run_tmem<1>(cyc, sink, warps, "st 2 x (32x32b.x32) + wait")) return 1;

@@ -230,11 +230,15 @@ TFHE_HD void load_rot_diffs(uint32_t (&d)[16], const uint32_t *acc, int atil, ui
     }
 }
 // gadget digit of level l (shift sh = 32 - (l+1)*bgbit) as signed integer -> double
+// exact int32 -> double.  I2F.F64.S32 runs on the conversion unit, in parallel with the FP64 pipe.  (Measured: assembling
+// the double from its bit pattern + one DADD instead moves 96 operations per warp and CMUX step onto the FP64 pipe,
+// the busier of the two: 88.5 k instead of 90.9 k bootstraps/s.)
+TFHE_HD double int_to_double(int32_t x) { return (double)x; }
 TFHE_HD void digits_to_cplx(cplx (&v)[8], const uint32_t (&d)[16], int sh, uint32_t mask, uint32_t half_bg) {
 #pragma unroll
     for (int p = 0; p < 8; p++) {
-        v[p].re = (double)(int32_t)(((d[2 * p] >> sh) & mask) - half_bg);
-        v[p].im = (double)(int32_t)(((d[2 * p + 1] >> sh) & mask) - half_bg);
+        v[p].re = int_to_double((int32_t)(((d[2 * p] >> sh) & mask) - half_bg));
+        v[p].im = int_to_double((int32_t)(((d[2 * p + 1] >> sh) & mask) - half_bg));
     }
 }
 
