@@ -136,6 +136,30 @@ int tfhe_b200_reencrypt_batch(tfhe_b200_ctx *ctx, const uint32_t *in, uint32_t *
 /* Gates.notGate / copy (src/gates.zig:131-141): no bootstrap, out = -a. */
 int tfhe_b200_not_batch(tfhe_b200_ctx *ctx, const uint32_t *a, uint32_t *out, size_t B);
 
+/* ---- gate circuits: level-batched, device-resident ------------------------------------- */
+/* The reference evaluates a circuit (examples/add_two_numbers.zig:24-73: fullAdder, ripple-carry add) one
+ * Gates.* call after another (src/gates.zig:48-121).  Here a netlist is levelised once and every dependency
+ * level runs as ONE batched launch pair over (gates of the level) x (instances); wires never leave the device
+ * between levels and the level sequence is replayed as a CUDA graph.  Instances are independent, so a
+ * multi-device context shards them with no cross-device traffic.
+ * Wire ids: 0 .. n_inputs-1 are the circuit inputs, n_inputs + g is the output of gate g; gates are given in
+ * topological order.  TFHE_B200_WIRE_NOT on a wire reference is Gates.notGate (src/gates.zig:131-133) of that wire:
+ * free, folded into the consuming gate's linear part (or applied on the way out for a circuit output). */
+#define TFHE_B200_WIRE_NOT 0x80000000u
+typedef struct {
+    int32_t op;  /* tfhe_b200_gate */
+    uint32_t a;  /* wire id | TFHE_B200_WIRE_NOT */
+    uint32_t b;
+} tfhe_b200_gate_node;
+typedef struct tfhe_b200_circuit tfhe_b200_circuit;
+int tfhe_b200_circuit_create(tfhe_b200_ctx *ctx, const tfhe_b200_gate_node *gates, size_t n_gates, size_t n_inputs,
+                             const uint32_t *outputs, size_t n_outputs, tfhe_b200_circuit **out);
+void tfhe_b200_circuit_destroy(tfhe_b200_circuit *circuit);
+int tfhe_b200_circuit_info(const tfhe_b200_circuit *circuit, size_t *n_levels, size_t *max_level_width, size_t *n_gates);
+/* inputs: [n_inputs][instances][n+1], outputs: [n_outputs][instances][n+1] (host buffers, wire-major). */
+int tfhe_b200_circuit_run(tfhe_b200_ctx *ctx, tfhe_b200_circuit *circuit, const uint32_t *inputs, uint32_t *outputs,
+                          size_t instances);
+
 /* ---- hot path, device buffers (single device `dev` of the context, asynchronous) ------- */
 int tfhe_b200_gate_batch_device(tfhe_b200_ctx *ctx, int dev, int op, const int32_t *d_ops, const uint32_t *d_a,
                                 const uint32_t *d_b, uint32_t *d_out, size_t B);
@@ -157,7 +181,8 @@ double tfhe_b200_max_round_margin(tfhe_b200_ctx *ctx, int reset);
 /* number of kernels this library launched since the context was created (bench `gpu_launches`) */
 uint64_t tfhe_b200_launch_count(const tfhe_b200_ctx *ctx);
 /* tuning knobs (tests/bench): "kct" ciphertexts per CTA of the blind-rotation kernel (0 = default),
- * "use_tma" 0/1, "max_chunk" ciphertexts per launch, "timing" 0/1 (record CUDA events around K1/K2) */
+ * "use_tma" 0/1, "max_chunk" ciphertexts per launch, "timing" 0/1 (record CUDA events around K1/K2),
+ * "team" / "pipeline" K1 variants kept for A/B runs, "circuit_graph" 0/1 (CUDA-graph replay of circuit levels) */
 int tfhe_b200_set_tuning(tfhe_b200_ctx *ctx, const char *key, int value);
 /* with "timing" on: device time in ms of the last blind-rotation (which = 0) or key-switch (which = 1)
  * kernel enqueued on device `dev`, measured with CUDA events on the launching stream */

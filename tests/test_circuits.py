@@ -125,3 +125,104 @@ def test_device_resident_adder_equals_host_level_version():
         assert (total == x + y).all()
     finally:
         ctx.close()
+
+
+# ---- native circuit executor (tfhe_b200_circuit_*) ----------------------------------------------------------
+def _eval_netlist_plain(gates, n_inputs, outputs, in_bits):
+    """reference semantics of a netlist on plaintext bits (gates.zig:48-121 truth tables, conftest.TRUTH)"""
+    from conftest import TRUTH
+    NOT = 0x80000000
+    wires = [np.asarray(b, np.uint8) for b in in_bits]
+    ref = lambda w: (1 - wires[w & ~NOT]) if (w & NOT) else wires[w & ~NOT]
+    for op, a, b in gates:
+        wires.append(np.asarray(TRUTH[op](ref(a), ref(b)), np.uint8))
+    return [ref(o) for o in outputs]
+
+
+def test_adder_netlist_is_the_reference_full_adder_chain():
+    from tfhe_b200 import circuits
+    W = 16
+    gates, n_in, outs = circuits.ripple_carry_netlist(W)
+    assert len(gates) == 5 * W and n_in == 2 * W + 1 and len(outs) == W + 1      # add_two_numbers.zig:24-73
+    for k, (_, a, b) in enumerate(gates):
+        assert max(a, b) < n_in + k                                              # topological
+    rng = np.random.default_rng(5)
+    B = 50
+    x = rng.integers(0, 2**16, B); y = rng.integers(0, 2**16, B); cin = rng.integers(0, 2, B)
+    x[0], y[0], cin[0] = 402, 304, 0
+    bits = list(circuits.to_bits(x, W)) + list(circuits.to_bits(y, W)) + [cin.astype(np.uint8)]
+    o = _eval_netlist_plain(gates, n_in, outs, bits)
+    total = circuits.from_bits(np.stack(o[:W])) + (o[W].astype(np.uint64) << np.uint64(W))
+    assert (total == x + y + cin).all() and total[0] == 706
+
+
+@pytest.mark.gpu
+def test_native_circuit_equals_level_batched_python_and_oracle():
+    import tfhe_b200
+    from tfhe_b200 import circuits
+    orc = O.Oracle("128"); keys = keys_for("128")
+    ctx = tfhe_b200.Context("128", devices=[0])
+    try:
+        ctx.load_key(keys.bsk, keys.ksk, keys.offset)
+        rng = np.random.default_rng(7)
+        W, B = 4, 37                                          # ragged instance count
+        x = rng.integers(0, 2**W, B); y = rng.integers(0, 2**W, B)
+        enc = lambda bits, seed: np.stack([orc.encrypt_bools(bits[i], keys, seed + i) for i in range(W)])
+        ca, cb = enc(circuits.to_bits(x, W), 100), enc(circuits.to_bits(y, W), 200)
+        cin = orc.encrypt_bools(np.zeros(B, np.uint8), keys, 300)
+        s_py, c_py, gates, levels = circuits.ripple_carry_add(ctx, ca, cb, cin)
+        s_nat, c_nat, circ = circuits.ripple_carry_add_native(ctx, ca, cb, cin)
+        assert circ.levels == 1 + 2 * W == levels and circ.n_gates == 5 * W and circ.max_width == 2 * W
+        assert (s_nat == s_py).all() and (c_nat == c_py).all()            # every ciphertext word
+        dec = np.stack([orc.decrypt_bools(s_nat[i], keys) for i in range(W)])
+        total = circuits.from_bits(dec) + (orc.decrypt_bools(c_nat, keys).astype(np.uint64) << np.uint64(W))
+        assert (total == x + y).all()
+        # graph replay (second run, same size), then eager levels: identical bits
+        s2, c2, _ = circuits.ripple_carry_add_native(ctx, ca, cb, cin, circ)
+        ctx.set_tuning("circuit_graph", 0)
+        s3, c3, _ = circuits.ripple_carry_add_native(ctx, ca, cb, cin, circ)
+        assert (s2 == s_nat).all() and (c2 == c_nat).all() and (s3 == s_nat).all() and (c3 == c_nat).all()
+        ctx.set_tuning("circuit_graph", 1)
+        # a different instance count re-captures
+        s4, c4, _ = circuits.ripple_carry_add_native(ctx, ca[:, :5], cb[:, :5], cin[:5], circ)
+        assert (s4 == s_nat[:, :5]).all() and (c4 == c_nat[:5]).all()
+        circ.close()
+    finally:
+        ctx.close()
+
+
+@pytest.mark.gpu
+def test_native_circuit_not_folding_and_all_gates_vs_oracle():
+    """NOT wires are folded into the consumer's linear part (gates.zig:131-133 then 48-121): every opcode with
+    plain and negated operands, and a negated circuit output, word for word against the oracle"""
+    import tfhe_b200
+    orc = O.Oracle("128"); keys = keys_for("128")
+    ctx = tfhe_b200.Context("128", devices=[0])
+    try:
+        ctx.load_key(keys.bsk, keys.ksk, keys.offset)
+        NOT = tfhe_b200.WIRE_NOT
+        B = 3
+        a_bits = np.array([0, 1, 1], np.uint8); b_bits = np.array([1, 0, 1], np.uint8)
+        ca = orc.encrypt_bools(a_bits, keys, 11); cb = orc.encrypt_bools(b_bits, keys, 12)
+        gates = [(op, 0, 1) for op in range(10)] + [(op, 0 | NOT, 1) for op in range(10)] + [(O.AND, 0, 1 | NOT)]
+        gates.append((O.OR, 2 + 2, 2 + 12 | NOT))                 # second level: OR(AND(a,b), NOT ANDNY... any wires)
+        outs = list(range(2, 2 + len(gates))) + [(2 + 3) | NOT, 0 | NOT]
+        circ = tfhe_b200.Circuit(ctx, gates, 2, outs)
+        assert circ.levels == 2
+        got = circ.run(np.stack([ca, cb]))
+        neg = lambda c: (0 - c.astype(np.int64)).astype(np.uint32)
+        wires = [ca, cb]
+        ref = lambda w: neg(wires[w & ~NOT]) if (w & NOT) else wires[w & ~NOT]
+        for op, a, b in gates:
+            wires.append(orc.gate_batch(op, ref(a), ref(b), keys))
+        for k, o in enumerate(outs):
+            assert (got[k] == ref(o)).all(), f"output {k}"
+        circ.close()
+        # error behaviour: forward reference, bad opcode, bad output wire
+        for bad in ([(0, 0, 3)], [(17, 0, 1)]):
+            with pytest.raises(tfhe_b200.TfheB200Error):
+                tfhe_b200.Circuit(ctx, bad, 2, [2])
+        with pytest.raises(tfhe_b200.TfheB200Error):
+            tfhe_b200.Circuit(ctx, [(0, 0, 1)], 2, [9])
+    finally:
+        ctx.close()

@@ -25,14 +25,24 @@ ca, cb = enc(circuits.to_bits(x, W)), enc(circuits.to_bits(y, W))
 cin = HK.encrypt_bools(np.zeros(B, np.uint8), params, sk, rng)
 t = lambda a: torch.from_numpy(a.view(np.int32)).cuda()
 da, db, dc = t(ca), t(cb), t(cin)
-for name in ("host-level", "device-resident"):
+circ = None
+for name in ("host-level", "device-resident", "native circuit, 1 lane (CUDA graph)", "native circuit, 1 lane (eager levels)",
+             "native circuit, 2 lanes (CUDA graph)", "native circuit, 4 lanes (CUDA graph)", "native circuit, 8 lanes (CUDA graph)"):
+    if "lane" in name:
+        lanes = int(name.split(",")[1].split()[0])
+        if circ is None or lanes != cur_lanes:
+            ctx.set_tuning("circuit_lanes", lanes)
+            circ, cur_lanes = None, lanes
     for rep in range(2):
         t0 = time.perf_counter()
         if name == "host-level":
             sums, carry, gates, levels = circuits.ripple_carry_add(ctx, ca, cb, cin)
-        else:
+        elif name == "device-resident":
             s_d, c_d = circuits.ripple_carry_add_device(ctx, da, db, dc)
             sums, carry = s_d.cpu().numpy().view(np.uint32), c_d.cpu().numpy().view(np.uint32)
+        else:
+            ctx.set_tuning("circuit_graph", 1 if "graph" in name else 0)
+            sums, carry, circ = circuits.ripple_carry_add_native(ctx, ca, cb, cin, circ)
         dt = time.perf_counter() - t0
     dec = np.stack([HK.decrypt_bools(sums[i], sk) for i in range(W)])
     total = circuits.from_bits(dec) + (HK.decrypt_bools(carry, sk).astype(np.uint64) << np.uint64(W))

@@ -322,11 +322,10 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
 
     // ---- prologue: gate linear part (gates.zig:48-121) + modulus switch (trgsw.zig:297,312)
     {
-        const int op = P.ops ? P.ops[ct] : P.op;
-        const uint32_t *ia = P.in_a + ct * (size_t)(n + 1);
-        const uint32_t *ib = (op >= 0) ? P.in_b + ct * (size_t)(n + 1) : ia;
+        const GateOperands go = gate_operands(P, ct, n);
+        const int op = go.op;
         for (int i = t; i <= n; i += kGroupThreads) {
-            uint32_t lin = gate_linear(op, ia[i], ib[i]);
+            uint32_t lin = gate_linear_signed(go, i);
             if (i == n) lin += gate_constant(op);
             const uint32_t m = (uint32_t)(((unsigned long long)lin + (1u << 20)) >> 21);   // in [0, 2N]
             atil[i] = (uint16_t)((i == n) ? (2 * kN - m) : m);
@@ -529,11 +528,10 @@ __global__ void __launch_bounds__(2 * L * kGroupThreads, 1) blind_rotate_latency
         for (int p = 1; p < 8; p++) { tw2.w[p - 1] = P.tw2[tw2_index(p, lo)]; tw3.w[p - 1] = P.tw3[tw3_index(p, t)]; }
     }
     {   // prologue: gate linear part + modulus switch, whole CTA
-        const int op = P.ops ? P.ops[ct] : P.op;
-        const uint32_t *ia = P.in_a + ct * (size_t)(n + 1);
-        const uint32_t *ib = (op >= 0) ? P.in_b + ct * (size_t)(n + 1) : ia;
+        const GateOperands go = gate_operands(P, ct, n);
+        const int op = go.op;
         for (int i = tid; i <= n; i += G * kGroupThreads) {
-            uint32_t lin = gate_linear(op, ia[i], ib[i]);
+            uint32_t lin = gate_linear_signed(go, i);
             if (i == n) lin += gate_constant(op);
             const uint32_t m = (uint32_t)(((unsigned long long)lin + (1u << 20)) >> 21);
             atil[i] = (uint16_t)((i == n) ? (2 * kN - m) : m);
@@ -722,11 +720,10 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_swp_kerne
 
     // ---- prologue: gate linear part (gates.zig:48-121) + modulus switch (trgsw.zig:297,312)
     {
-        const int op = P.ops ? P.ops[ct] : P.op;
-        const uint32_t *ia = P.in_a + ct * (size_t)(n + 1);
-        const uint32_t *ib = (op >= 0) ? P.in_b + ct * (size_t)(n + 1) : ia;
+        const GateOperands go = gate_operands(P, ct, n);
+        const int op = go.op;
         for (int i = t; i <= n; i += kGroupThreads) {
-            uint32_t lin = gate_linear(op, ia[i], ib[i]);
+            uint32_t lin = gate_linear_signed(go, i);
             if (i == n) lin += gate_constant(op);
             const uint32_t m = (uint32_t)(((unsigned long long)lin + (1u << 20)) >> 21);   // in [0, 2N]
             atil[i] = (uint16_t)((i == n) ? (2 * kN - m) : m);
@@ -970,6 +967,7 @@ cudaError_t launch_blind_rotate(const BrArgs &a, const BrTuning &tune, bool trac
         }
     }
     int kct = tune.kct;
+    if (kct <= 0 && tune.concurrent != 0) kct = 4;   // densest CTA (ciphertexts per SM-second); idle SMs go to the other lanes
     if (kct <= 0) {
         // minimise (number of CTA waves) x (time of one CTA at that width); CTA times measured on B200 at n = 700
         // (profiles/r01_first_light*.log, profiles/r01_wave_scaling.log): 1 or 2 ciphertexts 4.5 ms, 3: 6.1 ms, 4: 6.5 ms.

@@ -68,11 +68,10 @@ __global__ void __launch_bounds__(kThreads, 2) blind_rotate_exact_kernel(const B
     const double *fwd_re = tab + 2 * kTabStride, *fwd_im = tab + 3 * kTabStride;
     const double *inv_re = tab + 4 * kTabStride, *inv_im = tab + 5 * kTabStride;
     {
-        const int op = P.ops ? P.ops[ct] : P.op;
-        const uint32_t *ia = P.in_a + ct * (size_t)(n + 1);
-        const uint32_t *ib = (op >= 0) ? P.in_b + ct * (size_t)(n + 1) : ia;
+        const GateOperands go = gate_operands(P, ct, n);
+        const int op = go.op;
         for (int i = j; i <= n; i += kThreads) {
-            uint32_t lin = gate_linear(op, ia[i], ib[i]);
+            uint32_t lin = gate_linear_signed(go, i);
             if (i == n) lin += gate_constant(op);
             const uint32_t m = (uint32_t)(((unsigned long long)lin + (1u << 20)) >> 21);
             atil[i] = (uint16_t)((i == n) ? (2 * kN - m) : m);

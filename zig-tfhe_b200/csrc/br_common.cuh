@@ -129,5 +129,35 @@ __device__ __forceinline__ uint32_t gate_constant(int op) {
     }
 }
 
+// Operands of item `ct`: plain batch (rows ct of in_a / in_b) or one gate of a circuit level (rows of the wire store).
+// neg bit 0 / 1: operand a / b enters through Gates.notGate (src/gates.zig:131-133), i.e. negated coefficient-wise.
+struct GateOperands {
+    const uint32_t *a, *b;
+    int op;
+    uint32_t neg;
+};
+template <class Args>
+__device__ __forceinline__ GateOperands gate_operands(const Args &P, size_t ct, int n) {
+    GateOperands g;
+    const size_t w = (size_t)n + 1;
+    if (P.lvl_a) {
+        const uint32_t gi = (uint32_t)(ct / P.inst), k = (uint32_t)(ct - (size_t)gi * P.inst);
+        const uint32_t wa = P.lvl_a[gi], wb = P.lvl_b[gi];
+        g.op = P.lvl_ops[gi];
+        g.a = P.in_a + ((size_t)(wa & 0x7fffffffu) * P.inst + k) * w;
+        g.b = P.in_a + ((size_t)(wb & 0x7fffffffu) * P.inst + k) * w;
+        g.neg = (wa >> 31) | ((wb >> 31) << 1);
+    } else {
+        g.op = P.ops ? P.ops[ct] : P.op;
+        g.a = P.in_a + ct * w;
+        g.b = (g.op >= 0) ? P.in_b + ct * w : g.a;
+        g.neg = 0u;
+    }
+    return g;
+}
+__device__ __forceinline__ uint32_t gate_linear_signed(const GateOperands &g, int i) {
+    const uint32_t a = g.a[i], b = g.b[i];
+    return gate_linear(g.op, (g.neg & 1u) ? 0u - a : a, (g.neg & 2u) ? 0u - b : b);
+}
 
 }  // namespace tfhe_b200

@@ -57,6 +57,8 @@ struct tfhe_b200_ctx {
     bool timing = false;
     int ks_tile = 0, ks_vec = 0;          // key-switch tuning overrides (0 = automatic)
     size_t max_chunk = (size_t)1 << 18;   // ciphertexts per device per launch
+    bool circuit_graph = true;            // replay a circuit's level sequence as one CUDA graph
+    int circuit_lanes = 4;                // independent instance groups per device, each on its own stream (set before circuit_create)
 };
 
 namespace {
@@ -95,8 +97,15 @@ bool wide_round(const tfhe_b200_params &p) {
 }
 
 // K1 (+K2) on device buffers of one device
+struct LevelRef {            // one dependency level of a circuit: operands are wire rows of d_a (see BrArgs)
+    const int32_t *ops;
+    const uint32_t *a, *b;
+    uint32_t inst;
+};
+
 int run_device(tfhe_b200_ctx *c, Device &d, int op, const int32_t *d_ops, const uint32_t *d_a, const uint32_t *d_b, uint32_t *d_lv0,
-               uint32_t *d_lv1_out, uint32_t *d_trlwe, size_t B, const uint32_t *d_tv, int tv_per_item) {
+               uint32_t *d_lv1_out, uint32_t *d_trlwe, size_t B, const uint32_t *d_tv, int tv_per_item,
+               const LevelRef *lvl = nullptr, bool concurrent = false) {
     if (!c->has_key) return fail(c, TFHE_B200_ERR_NO_KEY, "no cloud key loaded");
     if (B == 0) return 0;
     CU(c, cudaSetDevice(d.id));
@@ -107,6 +116,7 @@ int run_device(tfhe_b200_ctx *c, Device &d, int op, const int32_t *d_ops, const 
     }
     BrArgs A{};
     A.in_a = d_a; A.in_b = d_b; A.ops = d_ops; A.op = op;
+    if (lvl) { A.lvl_ops = lvl->ops; A.lvl_a = lvl->a; A.lvl_b = lvl->b; A.inst = lvl->inst; }
     A.bsk = d.bsk; A.tw2 = d.tw2; A.tw3 = d.tw3;
     A.testvec = d_tv; A.tv_per_item = tv_per_item;
     A.out_lv1 = lv1; A.out_trlwe = d_trlwe;
@@ -120,6 +130,7 @@ int run_device(tfhe_b200_ctx *c, Device &d, int op, const int32_t *d_ops, const 
     } else {
         BrTuning tune = c->tune;
         tune.sm_count = d.sm_count;
+        tune.concurrent = concurrent ? 1 : 0;
         CU(c, launch_blind_rotate(A, tune, c->track_margin, d.stream, &c->launches));
     }
     if (c->timing) CU(c, cudaEventRecord(d.ev[1], d.stream));
@@ -257,6 +268,81 @@ int upload_key_device(tfhe_b200_ctx *c, Device &d, const double *src_bsk, bool b
         CU(c, cudaStreamSynchronize(d.stream));
         if (stg) CU(c, cudaFree(stg));
     }
+    return 0;
+}
+
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+// Gate circuits: a netlist levelised once, every dependency level = one K1 + one K2 launch over
+// (gates of the level) x (instances), all wires resident on the device, the level sequence captured in a CUDA graph.
+struct tfhe_b200_circuit {
+    tfhe_b200_ctx *ctx = nullptr;
+    size_t n_inputs = 0, n_gates = 0, n_slots = 0, max_width = 0;
+    struct Level { uint32_t first_slot, G; size_t off; };
+    std::vector<Level> levels;
+    std::vector<int32_t> ops;        // level-sorted gate tables (slot references, bit 31 = NOT)
+    std::vector<uint32_t> wa, wb;
+    std::vector<uint32_t> outputs;   // slot references, bit 31 = NOT
+    // One entry per (device, lane).  Lanes are independent groups of instances running the same level sequence on their
+    // own streams: the tail wave of one lane's level overlaps the head of another's (a level of the 16-bit adder over
+    // 1,024 instances is only 1.7 or 3.5 waves of K1 CTAs), and one lane's key switch runs beside another's blind rotation.
+    struct PerDev {
+        int32_t *d_ops = nullptr;        // gate tables (owned by lane 0 of the device, shared by its other lanes)
+        uint32_t *d_a = nullptr, *d_b = nullptr;
+        cudaStream_t stream = nullptr;   // lane 0: the device's stream; others: owned
+        bool owns_stream = false, owns_tables = false;
+        Buf wires, lv1, neg;
+        cudaGraphExec_t graph = nullptr;
+        size_t graph_inst = 0;
+        uint64_t graph_launches = 0;
+        bool graph_failed = false;
+    };
+    std::vector<PerDev> dev;
+    int lanes = 1;
+};
+
+namespace {
+
+int circuit_levels(tfhe_b200_ctx *c, tfhe_b200_circuit *q, Device &dev, tfhe_b200_circuit::PerDev &pd, size_t inst) {
+    const size_t w0 = (size_t)c->prm.n + 1;
+    uint32_t *wires = (uint32_t *)pd.wires.p;
+    Device d = dev;              // same keys and tables, this lane's stream
+    d.stream = pd.stream;
+    for (const auto &lv : q->levels) {
+        LevelRef ref{pd.d_ops + lv.off, pd.d_a + lv.off, pd.d_b + lv.off, (uint32_t)inst};
+        if (int r = run_device(c, d, 0, nullptr, wires, nullptr, wires + (size_t)lv.first_slot * inst * w0, (uint32_t *)pd.lv1.p, nullptr,
+                               (size_t)lv.G * inst, nullptr, 0, &ref, q->lanes > 1))
+            return r;
+    }
+    return 0;
+}
+
+// enqueue every level of the circuit for `inst` instances whose input wires are already in pd.wires
+int circuit_enqueue(tfhe_b200_ctx *c, tfhe_b200_circuit *q, Device &d, tfhe_b200_circuit::PerDev &pd, size_t inst) {
+    if (!c->circuit_graph || c->timing || pd.graph_failed) return circuit_levels(c, q, d, pd, inst);
+    if (!pd.graph || pd.graph_inst != inst) {
+        if (pd.graph) { cudaGraphExecDestroy(pd.graph); pd.graph = nullptr; }
+        const uint64_t before = c->launches;
+        cudaGraph_t g = nullptr;
+        bool ok = cudaStreamBeginCapture(pd.stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        int r = ok ? circuit_levels(c, q, d, pd, inst) : 0;
+        if (ok) ok = cudaStreamEndCapture(pd.stream, &g) == cudaSuccess && r == 0 && g != nullptr;
+        if (ok) ok = cudaGraphInstantiate(&pd.graph, g, 0) == cudaSuccess;
+        if (g) cudaGraphDestroy(g);
+        pd.graph_launches = c->launches - before;
+        c->launches = before;
+        if (!ok) {               // capture refused: run the levels eagerly from now on
+            cudaGetLastError();
+            pd.graph = nullptr;
+            pd.graph_failed = true;
+            return circuit_levels(c, q, d, pd, inst);
+        }
+        pd.graph_inst = inst;
+    }
+    CU(c, cudaGraphLaunch(pd.graph, pd.stream));
+    c->launches += pd.graph_launches;
     return 0;
 }
 
@@ -497,6 +583,169 @@ int tfhe_b200_keyswitch_batch_device(tfhe_b200_ctx *c, int dev, const uint32_t *
     return 0;
 }
 
+
+int tfhe_b200_circuit_create(tfhe_b200_ctx *c, const tfhe_b200_gate_node *gates, size_t n_gates, size_t n_inputs,
+                             const uint32_t *outputs, size_t n_outputs, tfhe_b200_circuit **out) {
+    if (!c || !out || (!gates && n_gates) || (!outputs && n_outputs)) return fail(c, TFHE_B200_ERR_INVALID, "null argument");
+    *out = nullptr;
+    const size_t n_wires = n_inputs + n_gates;
+    if (n_wires == 0 || n_wires >= 0x7fffffffu) return fail(c, TFHE_B200_ERR_INVALID, "bad circuit size");
+    const uint32_t kNot = TFHE_B200_WIRE_NOT;
+    std::vector<uint32_t> level(n_wires, 0);
+    uint32_t depth = 0;
+    for (size_t g = 0; g < n_gates; g++) {
+        const uint32_t a = gates[g].a & ~kNot, b = gates[g].b & ~kNot;
+        if (gates[g].op < 0 || gates[g].op > 9) return fail(c, TFHE_B200_ERR_INVALID, "gate %zu: bad opcode %d", g, gates[g].op);
+        if (a >= n_inputs + g || b >= n_inputs + g) return fail(c, TFHE_B200_ERR_INVALID, "gate %zu reads a wire defined later (not topological)", g);
+        level[n_inputs + g] = 1 + std::max(level[a], level[b]);
+        depth = std::max(depth, level[n_inputs + g]);
+    }
+    for (size_t o = 0; o < n_outputs; o++)
+        if ((outputs[o] & ~kNot) >= n_wires) return fail(c, TFHE_B200_ERR_INVALID, "output %zu: no such wire", o);
+    auto *q = new tfhe_b200_circuit();
+    q->ctx = c;
+    q->n_inputs = n_inputs; q->n_gates = n_gates; q->n_slots = n_wires;
+    // storage slots: inputs first, then gates level by level, so that a level's outputs are one contiguous block
+    std::vector<uint32_t> slot(n_wires);
+    for (size_t i = 0; i < n_inputs; i++) slot[i] = (uint32_t)i;
+    std::vector<std::vector<uint32_t>> by_level(depth + 1);
+    for (size_t g = 0; g < n_gates; g++) by_level[level[n_inputs + g]].push_back((uint32_t)g);
+    uint32_t next = (uint32_t)n_inputs;
+    for (uint32_t l = 1; l <= depth; l++) {
+        q->levels.push_back({next, (uint32_t)by_level[l].size(), q->ops.size()});
+        q->max_width = std::max(q->max_width, by_level[l].size());
+        for (uint32_t g : by_level[l]) {
+            slot[n_inputs + g] = next++;
+            q->ops.push_back(gates[g].op);
+            q->wa.push_back(gates[g].a);     // user wire ids for now
+            q->wb.push_back(gates[g].b);
+        }
+    }
+    for (size_t k = 0; k < q->wa.size(); k++) {
+        q->wa[k] = slot[q->wa[k] & ~kNot] | (q->wa[k] & kNot);
+        q->wb[k] = slot[q->wb[k] & ~kNot] | (q->wb[k] & kNot);
+    }
+    for (size_t o = 0; o < n_outputs; o++) q->outputs.push_back(slot[outputs[o] & ~kNot] | (outputs[o] & kNot));
+    q->lanes = std::max(1, std::min(c->circuit_lanes, 8));
+    q->dev.resize(c->devs.size() * q->lanes);
+    for (size_t k = 0; k < c->devs.size(); k++) {
+        auto &pd = q->dev[k * q->lanes];
+        const size_t nt = std::max<size_t>(q->ops.size(), 1);
+        pd.owns_tables = true;
+        pd.stream = c->devs[k].stream;
+        bool ok = cudaSetDevice(c->devs[k].id) == cudaSuccess && cudaMalloc(&pd.d_ops, nt * 4) == cudaSuccess &&
+                  cudaMalloc(&pd.d_a, nt * 4) == cudaSuccess && cudaMalloc(&pd.d_b, nt * 4) == cudaSuccess;
+        if (ok && !q->ops.empty())
+            ok = cudaMemcpy(pd.d_ops, q->ops.data(), q->ops.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+                 cudaMemcpy(pd.d_a, q->wa.data(), q->wa.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+                 cudaMemcpy(pd.d_b, q->wb.data(), q->wb.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+        for (int l = 1; ok && l < q->lanes; l++) {
+            auto &pl = q->dev[k * q->lanes + l];
+            pl.d_ops = pd.d_ops; pl.d_a = pd.d_a; pl.d_b = pd.d_b;
+            ok = cudaStreamCreateWithFlags(&pl.stream, cudaStreamNonBlocking) == cudaSuccess;
+            pl.owns_stream = ok;
+        }
+        if (!ok) {
+            tfhe_b200_circuit_destroy(q);
+            return fail(c, TFHE_B200_ERR_CUDA, "circuit tables: %s", cudaGetErrorString(cudaGetLastError()));
+        }
+    }
+    *out = q;
+    return 0;
+}
+
+void tfhe_b200_circuit_destroy(tfhe_b200_circuit *q) {
+    if (!q) return;
+    for (size_t v = 0; v < q->dev.size(); v++) {
+        auto &pd = q->dev[v];
+        cudaSetDevice(q->ctx->devs[v / q->lanes].id);
+        if (pd.stream) cudaStreamSynchronize(pd.stream);
+        if (pd.graph) cudaGraphExecDestroy(pd.graph);
+        if (pd.owns_tables)
+            for (void *p : {(void *)pd.d_ops, (void *)pd.d_a, (void *)pd.d_b})
+                if (p) cudaFree(p);
+        for (void *p : {pd.wires.p, pd.lv1.p, pd.neg.p})
+            if (p) cudaFree(p);
+        if (pd.owns_stream) cudaStreamDestroy(pd.stream);
+    }
+    delete q;
+}
+
+int tfhe_b200_circuit_info(const tfhe_b200_circuit *q, size_t *n_levels, size_t *max_level_width, size_t *n_gates) {
+    if (!q) return TFHE_B200_ERR_INVALID;
+    if (n_levels) *n_levels = q->levels.size();
+    if (max_level_width) *max_level_width = q->max_width;
+    if (n_gates) *n_gates = q->n_gates;
+    return 0;
+}
+
+int tfhe_b200_circuit_run(tfhe_b200_ctx *c, tfhe_b200_circuit *q, const uint32_t *inputs, uint32_t *outputs, size_t instances) {
+    if (!c || !q || q->ctx != c) return fail(c, TFHE_B200_ERR_INVALID, "circuit belongs to another context");
+    if (!c->has_key || !c->has_ksk) return fail(c, TFHE_B200_ERR_NO_KEY, "no cloud key loaded");
+    if (instances == 0) return 0;
+    if ((q->n_inputs && !inputs) || (!q->outputs.empty() && !outputs)) return fail(c, TFHE_B200_ERR_INVALID, "null buffer");
+    const size_t w0 = (size_t)c->prm.n + 1, w1 = (size_t)kN + 1;
+    const int nd = (int)c->devs.size(), nv = nd * q->lanes;
+    // instances per pass: bounded by the launch chunk and by ~8 GiB of wire storage per device
+    size_t per_pass = std::max<size_t>(1, c->max_chunk / std::max<size_t>(q->max_width, 1));
+    per_pass = std::min(per_pass, std::max<size_t>(1, ((size_t)8 << 30) / (q->n_slots * w0 * 4 * q->lanes)));
+    // contiguous instance ranges: first over devices, then over the lanes of a device
+    std::vector<size_t> hi(nv), pos(nv), cur(nv);
+    for (int k = 0; k < nd; k++) {
+        const size_t dlo = instances * k / nd, dhi = instances * (k + 1) / nd;
+        for (int l = 0; l < q->lanes; l++) {
+            pos[k * q->lanes + l] = dlo + (dhi - dlo) * l / q->lanes;
+            hi[k * q->lanes + l] = dlo + (dhi - dlo) * (l + 1) / q->lanes;
+        }
+    }
+    bool more = true;
+    while (more) {
+        more = false;
+        for (int v = 0; v < nv; v++) {          // phase 1: inputs + all levels in flight on every lane of every device
+            Device &d = c->devs[v / q->lanes];
+            auto &pd = q->dev[v];
+            const size_t inst = std::min(per_pass, hi[v] - pos[v]);
+            cur[v] = inst;
+            if (inst == 0) continue;
+            CU(c, cudaSetDevice(d.id));
+            const void *old_w = pd.wires.p, *old_l = pd.lv1.p;
+            if (int r = ensure(c, pd.wires, q->n_slots * inst * w0 * 4)) return r;
+            if (int r = ensure(c, pd.lv1, std::max<size_t>(q->max_width, 1) * inst * w1 * 4)) return r;
+            if ((old_w != pd.wires.p || old_l != pd.lv1.p) && pd.graph) { cudaGraphExecDestroy(pd.graph); pd.graph = nullptr; }
+            uint32_t *wires = (uint32_t *)pd.wires.p;
+            for (size_t i = 0; i < q->n_inputs; i++)
+                CU(c, cudaMemcpyAsync(wires + i * inst * w0, inputs + (i * instances + pos[v]) * w0, inst * w0 * 4, cudaMemcpyHostToDevice, pd.stream));
+            if (int r = circuit_enqueue(c, q, d, pd, inst)) return r;
+        }
+        for (int v = 0; v < nv; v++) {          // phase 2: results back (pageable D2H blocks the host per lane)
+            Device &d = c->devs[v / q->lanes];
+            auto &pd = q->dev[v];
+            const size_t inst = cur[v];
+            if (inst == 0) continue;
+            CU(c, cudaSetDevice(d.id));
+            const uint32_t *wires = (const uint32_t *)pd.wires.p;
+            for (size_t o = 0; o < q->outputs.size(); o++) {
+                const uint32_t ref = q->outputs[o];
+                const uint32_t *src = wires + (size_t)(ref & ~TFHE_B200_WIRE_NOT) * inst * w0;
+                if (ref & TFHE_B200_WIRE_NOT) {   // Gates.notGate of the wire (src/gates.zig:131-133)
+                    if (int r = ensure(c, pd.neg, inst * w0 * 4)) return r;
+                    CU(c, launch_negate(src, (uint32_t *)pd.neg.p, inst * w0, pd.stream, &c->launches));
+                    src = (const uint32_t *)pd.neg.p;
+                }
+                CU(c, cudaMemcpyAsync(outputs + (o * instances + pos[v]) * w0, src, inst * w0 * 4, cudaMemcpyDeviceToHost, pd.stream));
+                if (ref & TFHE_B200_WIRE_NOT) CU(c, cudaStreamSynchronize(pd.stream));   // pd.neg is reused by the next output
+            }
+        }
+        for (int v = 0; v < nv; v++) {
+            CU(c, cudaSetDevice(c->devs[v / q->lanes].id));
+            CU(c, cudaStreamSynchronize(q->dev[v].stream));
+            pos[v] += cur[v];
+            if (pos[v] < hi[v]) more = true;
+        }
+    }
+    return 0;
+}
+
 void *tfhe_b200_stream(tfhe_b200_ctx *c, int dev) {
     if (!c || dev < 0 || dev >= (int)c->devs.size()) return nullptr;
     return (void *)c->devs[dev].stream;
@@ -545,6 +794,8 @@ int tfhe_b200_set_tuning(tfhe_b200_ctx *c, const char *key, int value) {
     else if (!strcmp(key, "timing")) c->timing = value != 0;
     else if (!strcmp(key, "ks_tile")) c->ks_tile = value;
     else if (!strcmp(key, "ks_vec")) c->ks_vec = value;
+    else if (!strcmp(key, "circuit_graph")) c->circuit_graph = value != 0;
+    else if (!strcmp(key, "circuit_lanes")) c->circuit_lanes = value;
     else if (!strcmp(key, "max_chunk")) c->max_chunk = value > 0 ? (size_t)value : c->max_chunk;
     else return fail(c, TFHE_B200_ERR_INVALID, "unknown tuning key %s", key);
     return 0;

@@ -12,6 +12,11 @@ struct BrArgs {
     const uint32_t *in_a;   // [B][n+1]: first gate operand, or the ciphertext itself when op < 0
     const uint32_t *in_b;   // [B][n+1]: second gate operand (ignored when the opcode is < 0)
     const int32_t *ops;     // per-item opcode, or nullptr -> `op`
+    // circuit level (capi.cu, tfhe_b200_circuit_run): when lvl_a != nullptr, item ct = gate slot g * inst + instance k reads
+    // its operands from wire rows of in_a: row = (lvl_a[g] & 0x7fffffff) * inst + k; bit 31 = Gates.notGate of that wire
+    const int32_t *lvl_ops;
+    const uint32_t *lvl_a, *lvl_b;
+    uint32_t inst;
     int op;                 // tfhe_b200_gate, or -1 = plain bootstrap input (no linear part)
     const cplx *bsk;        // device layout: [n*2L] chunks of [ab][q0][t] cplx (16 KiB each)
     const cplx *tw2;        // [7][8]
@@ -33,6 +38,7 @@ struct BrTuning {
     int sm_count = 0;   // SMs of the target device (wave-quantisation aware choice of kct)
     int latency_mode = 1;   // batches <= sm_count: one CTA per ciphertext, transforms of an iteration in parallel
     int pipeline = 0;   // 1: software-pipelined variant (split mbarrier exchanges; measured slower, kept for A/B), 0: bar.sync kernel
+    int concurrent = 0; // 1: other kernels share the GPU (circuit lanes): pick the CTA width by work per SM-second, not by waves
     int team = 0;       // ciphertexts sharing a warp in adjacent lanes (0 = default, 1, 2)
 };
 

@@ -119,6 +119,10 @@ def load_library():
         "tfhe_b200_set_tuning": (i32, [vp, C.c_char_p, i32]),
         "tfhe_b200_measure_fp64_tflops": (C.c_double, [vp, i32]),
         "tfhe_b200_last_kernel_ms": (C.c_double, [vp, i32, i32]),
+        "tfhe_b200_circuit_create": (i32, [vp, vp, sz, sz, vp, sz, vp]),
+        "tfhe_b200_circuit_destroy": (None, [vp]),
+        "tfhe_b200_circuit_info": (i32, [vp, vp, vp, vp]),
+        "tfhe_b200_circuit_run": (i32, [vp, vp, vp, vp, sz]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)   # AttributeError if the library does not export a declared symbol
@@ -137,6 +141,7 @@ EXPORTED_SYMBOLS = [
     "tfhe_b200_stream", "tfhe_b200_sync", "tfhe_b200_track_margin", "tfhe_b200_max_round_margin", "tfhe_b200_launch_count",
     "tfhe_b200_set_tuning", "tfhe_b200_measure_fp64_tflops", "tfhe_b200_last_kernel_ms",
     "tfhe_b200_load_reencryption_key", "tfhe_b200_reencrypt_batch",
+    "tfhe_b200_circuit_create", "tfhe_b200_circuit_destroy", "tfhe_b200_circuit_info", "tfhe_b200_circuit_run",
 ]
 
 
@@ -329,6 +334,56 @@ class Context:
 
     def measure_fp64_tflops(self, dev=0) -> float:
         return float(self.lib.tfhe_b200_measure_fp64_tflops(self.h, dev))
+
+
+
+WIRE_NOT = 0x80000000
+
+GATE_NODE = np.dtype([("op", np.int32), ("a", np.uint32), ("b", np.uint32)])
+
+
+class Circuit:
+    """A gate netlist compiled for a Context (tfhe_b200_circuit_*): levelised once, then every run evaluates all
+    `instances` independent input sets level by level on the GPU -- the batched form of a chain of Gates.* calls
+    such as examples/add_two_numbers.zig:24-73.
+
+    gates: sequence of (op, a, b) in topological order; wire ids 0..n_inputs-1 are inputs, n_inputs+g the output of
+    gate g; `wire | WIRE_NOT` feeds the Gates.notGate of a wire (free)."""
+
+    def __init__(self, ctx: "Context", gates, n_inputs: int, outputs):
+        self.ctx = ctx
+        g = np.zeros(len(gates), GATE_NODE)
+        for k, (op, a, b) in enumerate(gates):
+            g[k] = (int(op), int(a), int(b))
+        self.n_inputs = int(n_inputs)
+        self.outputs = np.ascontiguousarray(outputs, dtype=np.uint32)
+        h = C.c_void_p()
+        ctx._check(ctx.lib.tfhe_b200_circuit_create(ctx.h, _ptr(g), len(g), self.n_inputs, _ptr(self.outputs), len(self.outputs), C.byref(h)))
+        self.h = h
+        lv, wd, ng = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        ctx._check(ctx.lib.tfhe_b200_circuit_info(self.h, C.byref(lv), C.byref(wd), C.byref(ng)))
+        self.levels, self.max_width, self.n_gates = lv.value, wd.value, ng.value
+
+    def run(self, inputs):
+        """inputs: u32 [n_inputs][instances][n+1] -> outputs u32 [n_outputs][instances][n+1]"""
+        w = self.ctx.n + 1
+        x = np.ascontiguousarray(inputs, dtype=np.uint32)
+        assert x.ndim == 3 and x.shape[0] == self.n_inputs and x.shape[2] == w, x.shape
+        inst = x.shape[1]
+        out = np.empty((len(self.outputs), inst, w), np.uint32)
+        self.ctx._check(self.ctx.lib.tfhe_b200_circuit_run(self.ctx.h, self.h, _ptr(x), _ptr(out), inst))
+        return out
+
+    def close(self):
+        if self.h is not None and self.ctx.h is not None:
+            self.ctx.lib.tfhe_b200_circuit_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class GpuBootstrap:

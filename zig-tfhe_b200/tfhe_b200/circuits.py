@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from . import AND, OR, XOR, Context
+from . import AND, OR, XOR, Circuit, Context
 
 
 def to_bits(values, width: int) -> np.ndarray:
@@ -86,3 +86,36 @@ def ripple_carry_add_device(ctx: Context, d_a, d_b, d_cin, dev: int = 0):
         # keep every temporary alive until the stream has consumed it
         stream.synchronize()
     return sums, carry
+
+
+def ripple_carry_netlist(width: int):
+    """The reference's adder as a netlist for Circuit (examples/add_two_numbers.zig:24-73, fullAdder evaluated bit by
+    bit).  Inputs: a_0..a_{W-1}, b_0..b_{W-1}, cin (2W+1 wires); outputs: sum_0..sum_{W-1}, carry.
+    Returns (gates, n_inputs, outputs); 5W gates, 1 + 2W levels."""
+    W = width
+    n_inputs = 2 * W + 1
+    gates, outputs = [], []
+    carry = 2 * W                       # cin
+    for i in range(W):
+        a, b = i, W + i
+        g = n_inputs + len(gates)
+        gates.append((XOR, a, b))       # g     = a ^ b
+        gates.append((AND, a, b))       # g + 1 = a & b
+        gates.append((AND, g, carry))   # g + 2 = (a ^ b) & c
+        gates.append((XOR, g, carry))   # g + 3 = sum
+        gates.append((OR, g + 1, g + 2))  # g + 4 = carry out
+        outputs.append(g + 3)
+        carry = g + 4
+    outputs.append(carry)
+    return gates, n_inputs, outputs
+
+
+def ripple_carry_add_native(ctx: Context, a_bits: np.ndarray, b_bits: np.ndarray, cin: np.ndarray, circuit: Circuit | None = None):
+    """Same result as ripple_carry_add through the native circuit executor (one C call, wires stay on the GPU, levels
+    replayed as a CUDA graph).  Returns (sum_bits [W][B][n+1], carry [B][n+1], circuit)."""
+    W, B, w = a_bits.shape
+    if circuit is None:
+        gates, n_in, outs = ripple_carry_netlist(W)
+        circuit = Circuit(ctx, gates, n_in, outs)
+    out = circuit.run(np.concatenate([a_bits, b_bits, cin[None]]))
+    return out[:W], out[W], circuit
