@@ -182,7 +182,7 @@ double tfhe_b200_max_round_margin(tfhe_b200_ctx *ctx, int reset);
 uint64_t tfhe_b200_launch_count(const tfhe_b200_ctx *ctx);
 /* tuning knobs (tests/bench): "kct" ciphertexts per CTA of the blind-rotation kernel (0 = default),
  * "use_tma" 0/1, "max_chunk" ciphertexts per launch, "timing" 0/1 (record CUDA events around K1/K2),
- * "team" / "pipeline" K1 variants kept for A/B runs, "circuit_graph" 0/1 (CUDA-graph replay of circuit levels) */
+ * "team" (2: two ciphertexts per warp, a measured K1 variant kept for A/B runs), "circuit_graph" 0/1 (CUDA-graph replay of circuit levels) */
 int tfhe_b200_set_tuning(tfhe_b200_ctx *ctx, const char *key, int value);
 /* with "timing" on: device time in ms of the last blind-rotation (which = 0) or key-switch (which = 1)
  * kernel enqueued on device `dev`, measured with CUDA events on the launching stream */

@@ -611,310 +611,14 @@ __global__ void __launch_bounds__(2 * L * kGroupThreads, 1) blind_rotate_latency
     }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// K1 v3: software-pipelined throughput kernel.  Same arithmetic, layouts and key ring as blind_rotate_kernel
-// (bit-identical results); what changes is the order in which a warp issues its work, and who shares a warp.
-//
-//  * Split exchange barriers.  The cross-warp exchange X2 is guarded by mbarriers that a warp *arrives* on right
-//    after its stores and *waits* on only when it needs the partner's data.  In between it runs pass 1 of the
-//    NEXT digit transform (its registers are free: the current transform's data is in flight through shared
-//    memory), and the quarter-warp exchange X1 of that next transform is in turn covered by pass 3 + the
-//    pointwise MAC of the current one.  The two inverse transforms of an iteration are interleaved the same
-//    way, and the end-of-iteration barrier is split per accumulator half (a, b).  No extra registers: a
-//    transform whose data sits in an exchange buffer owns no registers.
-//  * Teams (TEAM = 2).  Two ciphertexts share each warp in adjacent lanes (lane = 2 j + c).  LDS.128 merges
-//    adjacent lane pairs that read the same 16 bytes (measured on B200, tools/microbench.cu M1 pattern 3: 2.0
-//    instead of 4.0 cycles per instruction), so the bootstrapping-key reads of the pointwise MAC -- identical
-//    for every ciphertext -- cost half the shared-memory wavefronts.  The two ciphertexts' buffers sit at
-//    offsets that differ by 64 (mod 128) bytes, which keeps every quarter-warp phase of the exchange
-//    stores/loads on 8 distinct 16-byte bank groups.
-struct TeamSync {
-    uint64_t *x2;      // [2]: one mbarrier per X2 buffer
-    uint64_t *acc_a;   // accumulator half a complete (round_accumulate of every team warp done)
-    uint64_t *acc_b;
-};
-
-// The producer's warp must never sit in a suspended try_wait: the warp it waits for may itself be waiting for a
-// key chunk only the producer can issue.  It spins on the non-blocking test_wait and keeps polling the ring.
-template <bool PRODUCER>
-__device__ __forceinline__ void team_wait(uint64_t *bar, uint32_t parity, Producer &pr, bool prod_warp) {
-    if (PRODUCER && prod_warp) {
-        while (!mbar_test_wait(bar, parity)) producer_poll(pr);
-    } else {
-        while (!mbar_try_wait(bar, parity)) {
-        }
-    }
-}
-__device__ __forceinline__ void team_signal(uint64_t *bar, int lane) {
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bar);
-}
-
-__host__ __device__ constexpr int swp_group_bytes(int n) {
-    // accumulator + X1 + two X2 buffers + modulus-switched mask; padded to 64 (mod 128) so that the two
-    // ciphertexts of a team occupy complementary bank halves
-    int b = 2 * kN * 4 + kX1Slots * 16 + 2 * kX2Slots * 16 + align16((n + 1) * 2);
-    while ((b & 127) != 64) b += 16;
-    return b;
-}
-constexpr int kSwpStages = 3;
-constexpr int kSwpHeaderBytes = 64 + 4 * 4 * 8;   // key-ring barriers + up to 4 teams x 4 mbarriers
-
-template <int KCT, int TEAM, bool MARGIN>
-__global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_swp_kernel(const BrArgs P) {
-    static_assert(KCT % TEAM == 0, "a team never straddles CTAs");
-    constexpr int kTeamWarps = 2 * TEAM;
-    constexpr int kTeamThreads = TEAM * kGroupThreads;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    cplx *bsk_ring = reinterpret_cast<cplx *>(smem_raw);
-    unsigned char *ptr = smem_raw + kSwpStages * kBskChunkBytes;
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(ptr);
-    uint64_t *empty_bar = full_bar + 4;
-    uint64_t *team_bars = full_bar + 8;
-    ptr += kSwpHeaderBytes;
-    const int n = P.n, L = P.L, bgbit = P.bgbit;
-    const int group_bytes = swp_group_bytes(n);
-
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int first_ct = blockIdx.x * KCT;
-    const int n_active = min(KCT, (int)P.B - first_ct);
-    const int active_teams = (n_active + TEAM - 1) / TEAM;
-
-    if (tid == 0) {
-        for (int s = 0; s < kSwpStages; s++) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], active_teams * kTeamWarps);   // one arrival per consumer warp
-        }
-        for (int b = 0; b < 4 * active_teams; b++) mbar_init(&team_bars[b], kTeamWarps);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    __syncthreads();
-
-    int team, g, t;
-    if (TEAM == 1) {
-        g = tid >> 6; t = tid & 63; team = g;
-    } else {
-        team = tid >> 7;
-        t = 16 * ((tid >> 5) & 3) + (lane >> 1);
-        g = 2 * team + (lane & 1);
-    }
-    if (team >= active_teams) return;            // whole warps
-    const bool live = g < n_active;              // TEAM = 2: the ghost half of a last, odd team mirrors its partner
-    const size_t ct = (size_t)first_ct + (live ? g : g - 1);
-    const int hi = t >> 3, lo = t & 7;
-    TeamSync ts;
-    ts.x2 = team_bars + 4 * team; ts.acc_a = ts.x2 + 2; ts.acc_b = ts.x2 + 3;
-    const int team_barid = 1 + team;
-
-    unsigned char *gb = ptr + (size_t)g * group_bytes;
-    uint32_t *acc_a = reinterpret_cast<uint32_t *>(gb);
-    uint32_t *acc_b = acc_a + kN;
-    cplx *x1 = reinterpret_cast<cplx *>(gb + 2 * kN * 4);
-    cplx *x2base = x1 + kX1Slots;
-    uint16_t *atil = reinterpret_cast<uint16_t *>(gb + 2 * kN * 4 + kX1Slots * 16 + 2 * kX2Slots * 16);
-
-    Tw2<kTwFull> tw2, tw3;
-#pragma unroll
-    for (int p = 1; p < 8; p++) { tw3.w[p - 1] = P.tw3[tw3_index(p, t)]; tw2.w[p - 1] = P.tw2[tw2_index(p, lo)]; }
-
-    // ---- prologue: gate linear part (gates.zig:48-121) + modulus switch (trgsw.zig:297,312)
-    {
-        const GateOperands go = gate_operands(P, ct, n);
-        const int op = go.op;
-        for (int i = t; i <= n; i += kGroupThreads) {
-            uint32_t lin = gate_linear_signed(go, i);
-            if (i == n) lin += gate_constant(op);
-            const uint32_t m = (uint32_t)(((unsigned long long)lin + (1u << 20)) >> 21);   // in [0, 2N]
-            atil[i] = (uint16_t)((i == n) ? (2 * kN - m) : m);
-        }
-    }
-    bar_sync(team_barid, kTeamThreads);
-    {   // acc = X^btil * testvec (trgsw.zig:300-306), stored in acc_pos order
-        const int btil = atil[n];
-        const uint32_t *tv = P.testvec ? P.testvec + (P.tv_per_item ? ct * (size_t)(2 * kN) : 0) : nullptr;
-        for (int j = t; j < kN; j += kGroupThreads) {
-            const int u = (j - btil) & (2 * kN - 1);
-            const uint32_t va = tv ? tv[u & (kN - 1)] : 0u;
-            const uint32_t vb = tv ? tv[kN + (u & (kN - 1))] : 0x20000000u;   // key.zig:134-145
-            acc_a[acc_pos(j)] = (u & kN) ? 0u - va : va;
-            acc_b[acc_pos(j)] = (u & kN) ? 0u - vb : vb;
-        }
-    }
-    bar_sync(team_barid, kTeamThreads);
-
-    const uint32_t mask = (1u << bgbit) - 1u, half_bg = 1u << (bgbit - 1);
-    const uint32_t offset = P.offset;
-    const int wide = P.wide_round;
-    const int twoL = 2 * L;
-    int stage = 0;
-    uint32_t phase = 0;
-    uint32_t xk = 0;              // X2 exchange counter: buffer xk & 1, barrier phase parity (xk >> 1) & 1
-    double margin = 0.0;
-    Producer pr;
-    pr.src = P.bsk; pr.ring = bsk_ring; pr.full_bar = full_bar; pr.empty_bar = empty_bar;
-    pr.remaining = n * twoL; pr.issued = 0; pr.stage = 0; pr.phase = 0; pr.stages = kSwpStages;
-    pr.active = tid == 0;
-    const bool prod_warp = tid < 32;
-    pr.policy = pr.active ? l2_policy_evict_last() : 0;
-#pragma unroll
-    for (int s = 0; s < kSwpStages; s++) producer_poll(pr);
-
-    // ---- n CMUX steps (trgsw.zig:311-330)
-    for (int i = 0; i < n; i++) {
-        const int at = atil[i];
-        const uint32_t prev = (uint32_t)(i - 1) & 1u;
-        cplx oa[8], ob[8], v[8];
-        uint32_t d[16];
-#pragma unroll
-        for (int q = 0; q < 8; q++) { oa[q] = cplx{0.0, 0.0}; ob[q] = cplx{0.0, 0.0}; }
-        if (i > 0) team_wait<true>(ts.acc_a, prev, pr, prod_warp);      // every team warp has added its part of acc_a
-        load_rot_diffs(d, acc_a, at, offset, hi, lo);
-        // stage A of transform 0: digits -> pass 1 -> X1
-        digits_to_cplx(v, d, 32 - bgbit, mask, half_bg);
-        fwd_pass1(v);
-        __syncwarp();
-#pragma unroll
-        for (int q = 0; q < 8; q++) x1[x1_slot(hi, q, lo)] = v[q];
-#pragma unroll 1
-        for (int k = 0; k < twoL; k++) {
-            // ---- stage B(k): X1 -> pass 2 -> X2, arrive
-            __syncwarp();
-#pragma unroll
-            for (int q = 0; q < 8; q++) v[q] = x1[x1_slot(hi, lo, q)];
-            fwd_pass(v, tw2.w, 1);
-            producer_poll(pr);
-            {
-                cplx *x2 = x2base + (xk & 1u) * kX2Slots;
-#pragma unroll
-                for (int q = 0; q < 8; q++) x2[x2_slot(lo, q, hi)] = v[q];
-            }
-            team_signal(&ts.x2[xk & 1u], lane);
-            // ---- stage A(k+1): the next transform's pass 1 runs while X2 of transform k is in flight
-            if (k + 1 < twoL) {
-                int l1 = k + 1;
-                if (l1 >= L) l1 -= L;
-                if (k + 1 == L) {      // digits of the b polynomial (trgsw.zig:211-217)
-                    if (i > 0) team_wait<true>(ts.acc_b, prev, pr, prod_warp);
-                    load_rot_diffs(d, acc_b, at, offset, hi, lo);
-                }
-                digits_to_cplx(v, d, 32 - (l1 + 1) * bgbit, mask, half_bg);
-                fwd_pass1(v);
-                __syncwarp();          // every lane of the quarter-warp has read X1 of transform k
-#pragma unroll
-                for (int q = 0; q < 8; q++) x1[x1_slot(hi, q, lo)] = v[q];
-            }
-            // ---- stage C(k): X2 -> pass 3 -> pointwise MAC with key chunk (i, k)
-            team_wait<true>(&ts.x2[xk & 1u], (xk >> 1) & 1u, pr, prod_warp);
-            {
-                const cplx *x2 = x2base + (xk & 1u) * kX2Slots;
-#pragma unroll
-                for (int q = 0; q < 8; q++) v[q] = x2[x2_slot(hi, lo, q)];
-            }
-            xk++;
-            fwd_pass(v, tw3.w, 1);
-            team_wait<true>(&full_bar[stage], phase, pr, prod_warp);
-            {
-                const cplx *chunk = bsk_ring + stage * kBskChunkCplx;
-#pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    cmac(oa[q], v[q], chunk[bsk_slot(0, q, t)]);
-                    cmac(ob[q], v[q], chunk[bsk_slot(1, q, t)]);
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[stage]);
-            producer_poll(pr);
-            if (++stage == kSwpStages) { stage = 0; phase ^= 1; }
-        }
-        // ---- the two inverse transforms, interleaved
-        const uint32_t ka = xk, kb = xk + 1;
-        xk += 2;
-        inv_pass(oa, tw3.w, 1);
-        {
-            cplx *x2 = x2base + (ka & 1u) * kX2Slots;
-#pragma unroll
-            for (int q = 0; q < 8; q++) x2[x2_slot(hi, lo, q)] = oa[q];
-        }
-        team_signal(&ts.x2[ka & 1u], lane);
-        inv_pass(ob, tw3.w, 1);
-        producer_poll(pr);
-        // every reader of the other X2 buffer (last forward transform) has arrived on exchange ka
-        team_wait<true>(&ts.x2[ka & 1u], (ka >> 1) & 1u, pr, prod_warp);
-        {
-            cplx *x2 = x2base + (kb & 1u) * kX2Slots;
-#pragma unroll
-            for (int q = 0; q < 8; q++) x2[x2_slot(hi, lo, q)] = ob[q];
-        }
-        team_signal(&ts.x2[kb & 1u], lane);
-        {
-            const cplx *x2 = x2base + (ka & 1u) * kX2Slots;
-#pragma unroll
-            for (int q = 0; q < 8; q++) oa[q] = x2[x2_slot(lo, q, hi)];
-        }
-        inv_pass(oa, tw2.w, 1);
-        __syncwarp();
-#pragma unroll
-        for (int q = 0; q < 8; q++) x1[x1_slot(hi, lo, q)] = oa[q];
-        team_wait<true>(&ts.x2[kb & 1u], (kb >> 1) & 1u, pr, prod_warp);
-        {
-            const cplx *x2 = x2base + (kb & 1u) * kX2Slots;
-#pragma unroll
-            for (int q = 0; q < 8; q++) ob[q] = x2[x2_slot(lo, q, hi)];
-        }
-        inv_pass(ob, tw2.w, 1);
-        __syncwarp();
-#pragma unroll
-        for (int q = 0; q < 8; q++) oa[q] = x1[x1_slot(hi, q, lo)];
-        __syncwarp();
-#pragma unroll
-        for (int q = 0; q < 8; q++) x1[x1_slot(hi, lo, q)] = ob[q];
-        inv_pass1(oa);
-        round_accumulate<MARGIN>(oa, acc_a, t, wide, margin);
-        team_signal(ts.acc_a, lane);
-#pragma unroll
-        for (int q = 0; q < 8; q++) ob[q] = x1[x1_slot(hi, q, lo)];
-        inv_pass1(ob);
-        round_accumulate<MARGIN>(ob, acc_b, t, wide, margin);
-        team_signal(ts.acc_b, lane);
-    }
-    {
-        const uint32_t last = (uint32_t)(n - 1) & 1u;
-        team_wait<false>(ts.acc_a, last, pr, false);
-        team_wait<false>(ts.acc_b, last, pr, false);
-    }
-
-    // ---- epilogue
-    if (live && P.out_trlwe) {
-        uint32_t *o = P.out_trlwe + ct * (size_t)(2 * kN);
-        for (int j = t; j < kN; j += kGroupThreads) { o[j] = acc_a[acc_pos(j)]; o[kN + j] = acc_b[acc_pos(j)]; }
-    }
-    if (live && P.out_lv1) {   // sampleExtractIndex(., 0): trlwe.zig:146-162
-        uint32_t *o = P.out_lv1 + ct * (size_t)(kN + 1);
-        for (int j = t; j <= kN; j += kGroupThreads)
-            o[j] = (j == 0) ? acc_a[0] : (j == kN) ? acc_b[0] : 0u - acc_a[acc_pos(kN - j)];
-    }
-    if (MARGIN && P.margin_bits) {
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) margin = fmax(margin, __shfl_xor_sync(0xffffffffu, margin, s));
-        if (lane == 0) atomicMax(P.margin_bits, (unsigned long long)__double_as_longlong(margin));
-    }
-}
-
-template <int KCT, int TEAM, bool MARGIN>
-cudaError_t launch_swp_variant(const BrArgs &a, cudaStream_t s) {
-    const size_t smem = kSwpStages * kBskChunkBytes + kSwpHeaderBytes + (size_t)KCT * swp_group_bytes(a.n);
-    auto kern = blind_rotate_swp_kernel<KCT, TEAM, MARGIN>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    const unsigned grid = (a.B + KCT - 1) / KCT;
-    kern<<<grid, KCT * kGroupThreads, smem, s>>>(a);
-    return cudaGetLastError();
-}
-template <int KCT, int TEAM>
-cudaError_t launch_swp(const BrArgs &a, bool margin, cudaStream_t s) {
-    return margin ? launch_swp_variant<KCT, TEAM, true>(a, s) : launch_swp_variant<KCT, TEAM, false>(a, s);
-}
+// (Tangent-form twiddles -- w = c (1 + i t) with the scale c folded into the first butterfly layer, 72 instead of 80 FP64
+// operations per forward pass -- were built and measured as well: bit-identical results, 242 registers, 89.6 k instead of
+// 90.9 k bootstraps/s at KCT = 4.  Fewer FP64 instructions do not shorten the dependent chain a warp waits on.)
+// (A software-pipelined variant of the throughput kernel -- X2 exchanges guarded by split mbarrier arrive / wait so that
+// pass 1 of the next digit transform ran between the stores and the loads of the current one -- was built and measured:
+// bit-identical results, 84.6 k instead of 90.8 k bootstraps/s.  mbarrier try_wait polling costs more than bar.sync and the
+// exposed latency is that of the loads themselves, not of the barrier; see DESIGN.md section 4 and
+// profiles/r01_team_probe.log.  The code was removed again.)
 
 template <int L, bool MARGIN>
 cudaError_t launch_latency(const BrArgs &a, cudaStream_t s) {
@@ -982,15 +686,6 @@ cudaError_t launch_blind_rotate(const BrArgs &a, const BrTuning &tune, bool trac
         }
     }
     if (launches) (*launches)++;
-    if (tune.pipeline != 0 && tune.use_tma != 0 && kct <= 4) {
-        const bool team2 = tune.team == 2;
-        switch (kct) {
-            case 1: return launch_swp<1, 1>(a, track_margin, s);
-            case 2: return team2 ? launch_swp<2, 2>(a, track_margin, s) : launch_swp<2, 1>(a, track_margin, s);
-            case 3: return launch_swp<3, 1>(a, track_margin, s);
-            default: return team2 ? launch_swp<4, 2>(a, track_margin, s) : launch_swp<4, 1>(a, track_margin, s);
-        }
-    }
     if (tune.use_tma != 0 && (kct == 2 || kct == 4 || kct == 6) && tune.team == 2)
         return kct == 2 ? launch_team2<2>(a, track_margin, s) : kct == 4 ? launch_team2<4>(a, track_margin, s) : launch_team2<6>(a, track_margin, s);
     switch (kct) {

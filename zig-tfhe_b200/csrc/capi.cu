@@ -789,7 +789,6 @@ int tfhe_b200_set_tuning(tfhe_b200_ctx *c, const char *key, int value) {
     if (!strcmp(key, "kct")) c->tune.kct = value;
     else if (!strcmp(key, "use_tma")) c->tune.use_tma = value;
     else if (!strcmp(key, "latency_mode")) c->tune.latency_mode = value;
-    else if (!strcmp(key, "pipeline")) c->tune.pipeline = value;
     else if (!strcmp(key, "team")) c->tune.team = value;
     else if (!strcmp(key, "timing")) c->timing = value != 0;
     else if (!strcmp(key, "ks_tile")) c->ks_tile = value;

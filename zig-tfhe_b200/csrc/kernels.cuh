@@ -37,7 +37,6 @@ struct BrTuning {
     int use_tma = 1;    // stream key chunks with cp.async.bulk + mbarrier (0: direct global loads)
     int sm_count = 0;   // SMs of the target device (wave-quantisation aware choice of kct)
     int latency_mode = 1;   // batches <= sm_count: one CTA per ciphertext, transforms of an iteration in parallel
-    int pipeline = 0;   // 1: software-pipelined variant (split mbarrier exchanges; measured slower, kept for A/B), 0: bar.sync kernel
     int concurrent = 0; // 1: other kernels share the GPU (circuit lanes): pick the CTA width by work per SM-second, not by waves
     int team = 0;       // ciphertexts sharing a warp in adjacent lanes (0 = default, 1, 2)
 };
