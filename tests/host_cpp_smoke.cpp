@@ -39,11 +39,20 @@ int main(int argc, char **argv) {
         auto nand = tfhe_b200::batchNand(bs, in);
         auto mux = gates.muxNaive(in[0].first, in[0].second, in[1].first);
         auto boot = bs.bootstrap(in[0].first);
+        // 1-bit full adder (examples/add_two_numbers.zig:24-39) as a circuit over all `count` instances: a, b, cin = NOT a
+        auto adder = tfhe_b200::Circuit::rippleCarryAdder(bs, 1);
+        std::vector<uint32_t> wires;
+        wires.insert(wires.end(), a.begin(), a.end());
+        wires.insert(wires.end(), b.begin(), b.end());
+        for (size_t i = 0; i < a.size(); i++) wires.push_back(0u - a[i]);
+        auto sum_carry = adder.run(wires, count);
         FILE *f = std::fopen((dir + "/out.bin").c_str(), "wb");
         for (auto &c : nand) std::fwrite(c.data(), 4, w, f);
         std::fwrite(mux.data(), 4, w, f);
         std::fwrite(boot.data(), 4, w, f);
+        std::fwrite(sum_carry.data(), 4, sum_carry.size(), f);
         std::fclose(f);
+        if (adder.levels() != 3 || adder.gates() != 5) return 5;
         std::printf("ok strategy=%s count=%zu\n", gates.bootstrapStrategy(), count);
     } catch (const tfhe_b200::Error &e) {
         std::printf("error %d: %s\n", e.code, e.what());

@@ -47,3 +47,9 @@ def test_cpp_host_mirror_on_gpu():
     mux = orc.gate(O.OR, orc.gate(O.AND, ca[0], cb[0], keys), orc.gate(O.AND, orc.gate_not(ca[0]), ca[1], keys), keys)
     assert (out[3] == mux).all()
     assert (out[4] == orc.bootstrap(ca[0], keys)).all()
+    # Circuit::rippleCarryAdder(1) over the 3 instances with cin = NOT a: fullAdder gate by gate (add_two_numbers.zig:24-39)
+    cin = np.stack([orc.gate_not(ca[i]) for i in range(3)])
+    axb = orc.gate_batch(O.XOR, ca, cb, keys); ab = orc.gate_batch(O.AND, ca, cb, keys)
+    t = orc.gate_batch(O.AND, axb, cin, keys)
+    assert (out[5:8] == orc.gate_batch(O.XOR, axb, cin, keys)).all()
+    assert (out[8:11] == orc.gate_batch(O.OR, ab, t, keys)).all()

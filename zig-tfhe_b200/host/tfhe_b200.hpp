@@ -142,4 +142,52 @@ inline auto batchXor(const GpuBootstrap &b, const std::vector<std::pair<Cipherte
 inline auto batchNor(const GpuBootstrap &b, const std::vector<std::pair<Ciphertext, Ciphertext>> &in) { return batchGate(b, TFHE_B200_NOR, in); }
 inline auto batchXnor(const GpuBootstrap &b, const std::vector<std::pair<Ciphertext, Ciphertext>> &in) { return batchGate(b, TFHE_B200_XNOR, in); }
 
+// A gate netlist compiled for the device (tfhe_b200_circuit_*): the batched form of a chain of Gates.* calls.
+// Wire ids: 0..n_inputs-1 inputs, n_inputs + g = output of gate g; `w | kNot` = Gates.notGate of wire w (free).
+class Circuit {
+public:
+    static constexpr uint32_t kNot = TFHE_B200_WIRE_NOT;
+    Circuit(const GpuBootstrap &b, const std::vector<tfhe_b200_gate_node> &gates, size_t n_inputs, const std::vector<uint32_t> &outputs)
+        : b_(b), n_inputs_(n_inputs), n_outputs_(outputs.size()) {
+        b_.check(tfhe_b200_circuit_create(b_.ctx(), gates.data(), gates.size(), n_inputs, outputs.data(), outputs.size(), &c_));
+        tfhe_b200_circuit_info(c_, &levels_, &width_, &gates_);
+    }
+    ~Circuit() { tfhe_b200_circuit_destroy(c_); }
+    Circuit(const Circuit &) = delete;
+    Circuit &operator=(const Circuit &) = delete;
+    size_t levels() const { return levels_; }
+    size_t gates() const { return gates_; }
+    // inputs [n_inputs][instances][n+1] -> outputs [n_outputs][instances][n+1]
+    std::vector<uint32_t> run(const std::vector<uint32_t> &inputs, size_t instances) const {
+        std::vector<uint32_t> out(n_outputs_ * instances * b_.words());
+        b_.check(tfhe_b200_circuit_run(b_.ctx(), c_, inputs.data(), out.data(), instances));
+        return out;
+    }
+    // examples/add_two_numbers.zig:24-73 (fullAdder chained over `width` bits): inputs a_0.., b_0.., cin; outputs sum_0.., carry
+    static Circuit rippleCarryAdder(const GpuBootstrap &b, int width) {
+        std::vector<tfhe_b200_gate_node> g;
+        std::vector<uint32_t> outs;
+        const uint32_t n_in = 2 * width + 1;
+        uint32_t carry = 2 * width;
+        for (int i = 0; i < width; i++) {
+            const uint32_t a = i, bb = width + i, k = n_in + (uint32_t)g.size();
+            g.push_back({TFHE_B200_XOR, a, bb});
+            g.push_back({TFHE_B200_AND, a, bb});
+            g.push_back({TFHE_B200_AND, k, carry});
+            g.push_back({TFHE_B200_XOR, k, carry});
+            g.push_back({TFHE_B200_OR, k + 1, k + 2});
+            outs.push_back(k + 3);
+            carry = k + 4;
+        }
+        outs.push_back(carry);
+        return Circuit(b, g, n_in, outs);
+    }
+    Circuit(Circuit &&o) noexcept : b_(o.b_), c_(o.c_), n_inputs_(o.n_inputs_), n_outputs_(o.n_outputs_), levels_(o.levels_), width_(o.width_), gates_(o.gates_) { o.c_ = nullptr; }
+
+private:
+    const GpuBootstrap &b_;
+    tfhe_b200_circuit *c_ = nullptr;
+    size_t n_inputs_, n_outputs_, levels_ = 0, width_ = 0, gates_ = 0;
+};
+
 }  // namespace tfhe_b200

@@ -51,3 +51,13 @@ pub extern fn tfhe_b200_load_reencryption_key(ctx: *Ctx, key: [*]const u32, base
 pub extern fn tfhe_b200_reencrypt_batch(ctx: *Ctx, in: [*]const u32, out: [*]u32, count: usize) c_int;
 pub extern fn tfhe_b200_not_batch(ctx: *Ctx, a: [*]const u32, out: [*]u32, count: usize) c_int;
 pub extern fn tfhe_b200_sync(ctx: *Ctx) c_int;
+
+/// gate circuits (include/tfhe_b200.h): a netlist levelised once, every level one batched launch pair over
+/// (gates of the level) x (instances) -- the batched form of examples/add_two_numbers.zig:24-73
+pub const Circuit = opaque {};
+pub const wire_not: u32 = 0x80000000; // Gates.notGate of the referenced wire, folded into the consumer
+pub const GateNode = extern struct { op: i32, a: u32, b: u32 };
+pub extern fn tfhe_b200_circuit_create(ctx: *Ctx, gates: [*]const GateNode, n_gates: usize, n_inputs: usize, outputs: [*]const u32, n_outputs: usize, out: *?*Circuit) c_int;
+pub extern fn tfhe_b200_circuit_destroy(circuit: ?*Circuit) void;
+pub extern fn tfhe_b200_circuit_info(circuit: *const Circuit, n_levels: ?*usize, max_level_width: ?*usize, n_gates: ?*usize) c_int;
+pub extern fn tfhe_b200_circuit_run(ctx: *Ctx, circuit: *Circuit, inputs: [*]const u32, outputs: [*]u32, instances: usize) c_int;

@@ -108,4 +108,51 @@ pub const GpuBootstrap = struct {
         }
         return result;
     }
+
+    /// `count` independent W-bit additions in one call: the batched form of examples/add_two_numbers.zig:56-73 (`add`),
+    /// which chains fullAdder (:24-39) gate by gate.  a, b: [W][count] ciphertexts (LSB first), cin: [count];
+    /// returns [W + 1][count] (sum bits, then the carry), caller-freed.
+    pub fn batchAdd(
+        self: *const Self,
+        allocator: std.mem.Allocator,
+        comptime W: usize,
+        a: []const utils.Ciphertext,
+        b: []const utils.Ciphertext,
+        cin: []const utils.Ciphertext,
+    ) ![]utils.Ciphertext {
+        const count = cin.len;
+        std.debug.assert(a.len == W * count and b.len == W * count);
+        var nodes: [5 * W]cuda.GateNode = undefined;
+        var outs: [W + 1]u32 = undefined;
+        const n_in: u32 = 2 * W + 1;
+        var carry: u32 = 2 * W;
+        for (0..W) |i| {
+            const g: u32 = n_in + @as(u32, @intCast(5 * i));
+            nodes[5 * i + 0] = .{ .op = @intFromEnum(cuda.Gate.xor), .a = @intCast(i), .b = @intCast(W + i) };
+            nodes[5 * i + 1] = .{ .op = @intFromEnum(cuda.Gate.@"and"), .a = @intCast(i), .b = @intCast(W + i) };
+            nodes[5 * i + 2] = .{ .op = @intFromEnum(cuda.Gate.@"and"), .a = g, .b = carry };
+            nodes[5 * i + 3] = .{ .op = @intFromEnum(cuda.Gate.xor), .a = g, .b = carry };
+            nodes[5 * i + 4] = .{ .op = @intFromEnum(cuda.Gate.@"or"), .a = g + 1, .b = g + 2 };
+            outs[i] = g + 3;
+            carry = g + 4;
+        }
+        outs[W] = carry;
+        var circuit: ?*cuda.Circuit = null;
+        try cuda.check(cuda.tfhe_b200_circuit_create(self.ctx, &nodes, nodes.len, n_in, &outs, outs.len, &circuit));
+        defer cuda.tfhe_b200_circuit_destroy(circuit);
+        const in_words = try allocator.alloc(u32, n_in * count * CT_WORDS);
+        defer allocator.free(in_words);
+        for (a, 0..) |*c, i| @memcpy(in_words[i * CT_WORDS .. (i + 1) * CT_WORDS], &c.p);
+        for (b, 0..) |*c, i| @memcpy(in_words[(W * count + i) * CT_WORDS .. (W * count + i + 1) * CT_WORDS], &c.p);
+        for (cin, 0..) |*c, i| @memcpy(in_words[(2 * W * count + i) * CT_WORDS .. (2 * W * count + i + 1) * CT_WORDS], &c.p);
+        const out_words = try allocator.alloc(u32, (W + 1) * count * CT_WORDS);
+        defer allocator.free(out_words);
+        try cuda.check(cuda.tfhe_b200_circuit_run(self.ctx, circuit.?, in_words.ptr, out_words.ptr, count));
+        const result = try allocator.alloc(utils.Ciphertext, (W + 1) * count);
+        for (result, 0..) |*r, i| {
+            r.* = utils.Ciphertext.new();
+            @memcpy(&r.p, out_words[i * CT_WORDS .. (i + 1) * CT_WORDS]);
+        }
+        return result;
+    }
 };
