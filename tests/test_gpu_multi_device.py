@@ -30,3 +30,34 @@ def test_two_device_context_matches_single_device():
         assert (out2[::50] == orc.gate_batch(O.XOR, ca[::50], cb[::50], k)).all()
     finally:
         c1.close(); c2.close()
+
+
+def test_circuit_shards_instances_over_devices_and_lanes():
+    """tfhe_b200_circuit_run on a two-device context (4 lanes each): contiguous instance ranges per device and lane,
+    no cross-device traffic, same bits as one device with one lane"""
+    import torch
+    import tfhe_b200
+    from tfhe_b200 import circuits
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    orc = O.Oracle("128"); k = keys_for("128")
+    rng = np.random.default_rng(11)
+    W, B = 3, 29                                     # 29 instances over 2 devices x 4 lanes: ragged everywhere
+    x = rng.integers(0, 2**W, B); y = rng.integers(0, 2**W, B)
+    enc = lambda bits, seed: np.stack([orc.encrypt_bools(bits[i], k, seed + i) for i in range(W)])
+    ca, cb = enc(circuits.to_bits(x, W), 10), enc(circuits.to_bits(y, W), 20)
+    cin = orc.encrypt_bools(np.zeros(B, np.uint8), k, 30)
+    c2 = tfhe_b200.Context("128", devices=[0, 1]); c1 = tfhe_b200.Context("128", devices=[0])
+    try:
+        c1.set_tuning("circuit_lanes", 1)
+        for c in (c1, c2):
+            c.load_key(k.bsk, k.ksk, k.offset)
+        s2, carry2, q2 = circuits.ripple_carry_add_native(c2, ca, cb, cin)
+        s1, carry1, q1 = circuits.ripple_carry_add_native(c1, ca, cb, cin)
+        assert (s1 == s2).all() and (carry1 == carry2).all()
+        dec = np.stack([orc.decrypt_bools(s2[i], k) for i in range(W)])
+        total = circuits.from_bits(dec) + (orc.decrypt_bools(carry2, k).astype(np.uint64) << np.uint64(W))
+        assert (total == x + y).all()
+        q1.close(); q2.close()
+    finally:
+        c1.close(); c2.close()
