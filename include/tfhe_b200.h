@@ -116,6 +116,14 @@ int tfhe_b200_gate_batch_ops(tfhe_b200_ctx *ctx, const int32_t *ops, const uint3
  * i.e. the programmable (LUT) bootstrap the reference documents in src/lut.zig:42. */
 int tfhe_b200_bootstrap_batch(tfhe_b200_ctx *ctx, const uint32_t *in, uint32_t *out, size_t B,
                               const uint32_t *testvec, int tv_per_item);
+/* Programmable bootstrap from FUNCTION TABLES: lut.Generator.generateLookupTableFull (src/lut/generator.zig:150-191)
+ * runs on the device, then the `bootstrapLut` src/lut.zig:42 documents.  tables: [B][message_modulus] (per_item != 0)
+ * or [message_modulus] torus values, entry x = the output for message x (Encoder.encode(f(x)), src/lut/encoder.zig:66-73).
+ * Per-item tables cost message_modulus words of host-to-device traffic per item instead of an 8 KiB test vector. */
+int tfhe_b200_lut_bootstrap_batch(tfhe_b200_ctx *ctx, const uint32_t *in, uint32_t *out, size_t B, const uint32_t *tables,
+                                  int message_modulus, int per_item);
+/* parity tap: the device-built LookupTable.poly [2][N] of one table (src/lut/lookup_table.zig:16-20) */
+int tfhe_b200_lut_generate(tfhe_b200_ctx *ctx, const uint32_t *table, int message_modulus, uint32_t *testvec_out);
 /* VanillaBootstrap.bootstrapWithoutKeySwitch (src/bootstrap/vanilla.zig:58-69): blind rotation +
  * sampleExtractIndex2(.,0) (src/trlwe.zig:165-180); out [B][n+1]. */
 int tfhe_b200_bootstrap_no_keyswitch_batch(tfhe_b200_ctx *ctx, const uint32_t *in, uint32_t *out, size_t B);

@@ -46,3 +46,37 @@ def test_bootstrap_lut_on_gpu():
         assert (lut.bootstrap_lut(c, ct[0], table) == out[0]).all()
     finally:
         c.close()
+
+
+@pytest.mark.gpu
+def test_device_lut_generator_and_table_bootstrap():
+    """tfhe_b200_lut_generate == the host mirror == the oracle for every modulus (incl. non powers of two), and
+    tfhe_b200_lut_bootstrap_batch with per-item function tables == bootstrap with the host-built per-item test vectors"""
+    import tfhe_b200
+    from tfhe_b200 import lut
+    orc = O.Oracle("128"); k = keys_for("128")
+    c = tfhe_b200.Context("128", devices=[0])
+    try:
+        c.load_key(k.bsk, k.ksk, k.offset)
+        rng = np.random.default_rng(4)
+        for m in (1, 2, 3, 4, 5, 7, 8, 16, 31, 32, 100, 256, 1024):
+            table = rng.integers(0, 2**32, m, dtype=np.uint32)
+            gen = lut.Generator(m)
+            host = gen.generate_lookup_table_full(lambda x: int(table[x])).poly
+            assert (c.lut_generate(table) == host).all(), m
+        m = 4
+        enc = lut.Encoder(m)
+        B = 9
+        msgs = np.arange(B, dtype=np.uint32) % m
+        ct = orc.encrypt_lwe_messages(msgs, m, k, seed=78)
+        fs = [lambda x, a=a: (a * x + 1) % m for a in range(B)]              # a different function per item
+        tables = np.array([[enc.encode(f(x)) for x in range(m)] for f in fs], np.uint32)
+        tvs = np.stack([lut.Generator(m).generate_lookup_table(f).poly for f in fs])
+        out = c.lut_bootstrap_batch(ct, tables, per_item=True)
+        assert (out == c.bootstrap_batch(ct, tvs, tv_per_item=True)).all()
+        want = np.array([fs[i](int(msgs[i])) for i in range(B)])
+        assert (orc.decrypt_lwe_messages(out, m, k) == want).all()
+        one = c.lut_bootstrap_batch(ct, tables[2])                             # one table shared by the batch
+        assert (one == c.bootstrap_batch(ct, tvs[2])).all()
+    finally:
+        c.close()

@@ -35,7 +35,7 @@ struct Device {
     double *exact_tables = nullptr;   // make_exact_tables(), exact mode
     double *bsk_ref = nullptr;        // bootstrapping key in the reference layout (exact mode reads it as is)
     unsigned long long *margin_bits = nullptr;
-    Buf a, b, out, lv1, ops, tv, trlwe;
+    Buf a, b, out, lv1, ops, tv, trlwe, lut;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // K1 start, K1 end / K2 start, K2 end (timing mode)
     bool ev_valid = false;
 };
@@ -150,7 +150,7 @@ enum class Out { LV0, LV0_NOKS, LV1, TRLWE };
 
 // host-buffer driver: shard contiguously over devices, chunk, stage, launch, copy back
 int run_host(tfhe_b200_ctx *c, int op, const int32_t *ops, const uint32_t *a, const uint32_t *b, void *out, Out kind, size_t B,
-             const uint32_t *tv, int tv_per_item) {
+             const uint32_t *tv, int tv_per_item, int lut_m = 0) {   // lut_m > 0: `tv` holds function tables [B or 1][lut_m]
     if (!c) return TFHE_B200_ERR_INVALID;
     if (!c->has_key) return fail(c, TFHE_B200_ERR_NO_KEY, "no cloud key loaded");
     if (B == 0) return 0;
@@ -186,7 +186,14 @@ int run_host(tfhe_b200_ctx *c, int op, const int32_t *ops, const uint32_t *a, co
                 d_ops = (const int32_t *)d.ops.p;
             }
             const uint32_t *d_tv = nullptr;
-            if (tv) {
+            if (tv && lut_m > 0) {   // function tables in, test vectors built on the device
+                const size_t cnt = tv_per_item ? nb : 1;
+                if (int r = ensure(c, d.tv, cnt * wt * 4)) return r;
+                if (int r = ensure(c, d.lut, cnt * lut_m * 4)) return r;
+                CU(c, cudaMemcpyAsync(d.lut.p, tv + (tv_per_item ? off * lut_m : 0), cnt * lut_m * 4, cudaMemcpyHostToDevice, d.stream));
+                CU(c, launch_build_testvec((const uint32_t *)d.lut.p, lut_m, (uint32_t *)d.tv.p, cnt, d.stream, &c->launches));
+                d_tv = (const uint32_t *)d.tv.p;
+            } else if (tv) {
                 const size_t tvb = (tv_per_item ? nb : 1) * wt * 4;
                 if (int r = ensure(c, d.tv, tvb)) return r;
                 CU(c, cudaMemcpyAsync(d.tv.p, tv + (tv_per_item ? off * wt : 0), tvb, cudaMemcpyHostToDevice, d.stream));
@@ -402,7 +409,7 @@ void tfhe_b200_destroy(tfhe_b200_ctx *c) {
         cudaSetDevice(d.id);
         if (d.stream) cudaStreamSynchronize(d.stream);
         for (void *p : {(void *)d.bsk, (void *)d.ksk, (void *)d.reenc, (void *)d.tw2, (void *)d.tw3, (void *)d.exact_tables, (void *)d.bsk_ref, (void *)d.margin_bits, d.a.p, d.b.p,
-                        d.out.p, d.lv1.p, d.ops.p, d.tv.p, d.trlwe.p})
+                        d.out.p, d.lv1.p, d.ops.p, d.tv.p, d.trlwe.p, d.lut.p})
             if (p) cudaFree(p);
         for (cudaEvent_t e : d.ev) if (e) cudaEventDestroy(e);
         if (d.stream) cudaStreamDestroy(d.stream);
@@ -458,6 +465,25 @@ int tfhe_b200_gate_batch_ops(tfhe_b200_ctx *c, const int32_t *ops, const uint32_
 
 int tfhe_b200_bootstrap_batch(tfhe_b200_ctx *c, const uint32_t *in, uint32_t *out, size_t B, const uint32_t *tv, int tv_per_item) {
     return run_host(c, -1, nullptr, in, nullptr, out, Out::LV0, B, tv, tv_per_item);
+}
+
+int tfhe_b200_lut_bootstrap_batch(tfhe_b200_ctx *c, const uint32_t *in, uint32_t *out, size_t B, const uint32_t *tables, int message_modulus,
+                                  int per_item) {
+    if (!c || !tables || message_modulus < 1 || message_modulus > kN) return fail(c, TFHE_B200_ERR_INVALID, "bad lookup table");
+    return run_host(c, -1, nullptr, in, nullptr, out, Out::LV0, B, tables, per_item, message_modulus);
+}
+
+int tfhe_b200_lut_generate(tfhe_b200_ctx *c, const uint32_t *table, int message_modulus, uint32_t *testvec_out) {
+    if (!c || !table || !testvec_out || message_modulus < 1 || message_modulus > kN) return fail(c, TFHE_B200_ERR_INVALID, "bad lookup table");
+    Device &d = c->devs[0];
+    CU(c, cudaSetDevice(d.id));
+    if (int r = ensure(c, d.tv, (size_t)2 * kN * 4)) return r;
+    if (int r = ensure(c, d.lut, (size_t)message_modulus * 4)) return r;
+    CU(c, cudaMemcpyAsync(d.lut.p, table, (size_t)message_modulus * 4, cudaMemcpyHostToDevice, d.stream));
+    CU(c, launch_build_testvec((const uint32_t *)d.lut.p, message_modulus, (uint32_t *)d.tv.p, 1, d.stream, &c->launches));
+    CU(c, cudaMemcpyAsync(testvec_out, d.tv.p, (size_t)2 * kN * 4, cudaMemcpyDeviceToHost, d.stream));
+    CU(c, cudaStreamSynchronize(d.stream));
+    return 0;
 }
 
 int tfhe_b200_bootstrap_no_keyswitch_batch(tfhe_b200_ctx *c, const uint32_t *in, uint32_t *out, size_t B) {

@@ -62,6 +62,8 @@ cudaError_t launch_keyswitch(const KsArgs &a, int sm_count, cudaStream_t s, uint
 cudaError_t launch_permute_bsk(const double *ref_bsk, cplx *out, int n, int L, cudaStream_t s, uint64_t *launches);
 cudaError_t launch_repack_ksk(const uint32_t *ref_ksk, size_t ref_row_stride_u32, uint32_t *out, int n, int basebit, int iks_t,
                               int pitch, int in_dim, cudaStream_t s, uint64_t *launches);
+// test vectors [count][2][N] from function tables [count][m] of torus values (lut/generator.zig:158-191)
+cudaError_t launch_build_testvec(const uint32_t *tables, int m, uint32_t *out, size_t count, cudaStream_t s, uint64_t *launches);
 // K3: out = -a over [B][n+1]
 cudaError_t launch_negate(const uint32_t *a, uint32_t *out, size_t count, cudaStream_t s, uint64_t *launches);
 // first n entries + body of an lv1 sample -> TLWELv0-shaped "hybrid" sample (trlwe.zig:165-180)

@@ -24,6 +24,24 @@ __global__ void permute_bsk_kernel(const double *__restrict__ in, cplx *__restri
     }
 }
 
+// lut.Generator.generateLookupTableFullAssign (src/lut/generator.zig:158-191) on the device, one CTA per table:
+// raw[s] = table[x] for s in [divRound(x N, m), divRound((x+1) N, m)); rotated[i] = raw[(i + offset) mod N] with
+// offset = divRound(N, 2m); the last `offset` coefficients negated; a = 0, b = rotated.
+__global__ void build_testvec_kernel(const uint32_t *__restrict__ tables, int m, uint32_t *__restrict__ out) {
+    const uint32_t *table = tables + (size_t)blockIdx.x * m;
+    uint32_t *a = out + (size_t)blockIdx.x * 2 * kN, *b = a + kN;
+    const int offset = (kN + m) / (2 * m);                        // divRound(N, 2m), generator.zig:253-255
+    for (int i = threadIdx.x; i < kN; i += blockDim.x) {
+        const int s = (i + offset) & (kN - 1);
+        int x = (int)(((long long)s * m) / kN);                   // first guess, then settle on the divRound boundaries
+        while (x + 1 < m && (((long long)(x + 1) * kN + m / 2) / m) <= s) x++;
+        while (x > 0 && (((long long)x * kN + m / 2) / m) > s) x--;
+        const uint32_t v = table[x];
+        a[i] = 0u;
+        b[i] = (i >= kN - offset) ? 0u - v : v;
+    }
+}
+
 __global__ void fp64_peak_kernel(double *sink, int iters, double a, double b) {
     double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
     for (int i = 0; i < iters; i++) {
@@ -39,6 +57,13 @@ __global__ void fp64_peak_kernel(double *sink, int iters, double a, double b) {
 cudaError_t launch_permute_bsk(const double *ref_bsk, cplx *out, int n, int L, cudaStream_t s, uint64_t *launches) {
     const size_t polys = (size_t)n * 2 * L * 2;
     permute_bsk_kernel<<<(unsigned)polys, 256, 0, s>>>(ref_bsk, out, polys);
+    if (launches) (*launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_build_testvec(const uint32_t *tables, int m, uint32_t *out, size_t count, cudaStream_t s, uint64_t *launches) {
+    if (!count) return cudaSuccess;
+    build_testvec_kernel<<<(unsigned)count, 256, 0, s>>>(tables, m, out);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }

@@ -119,6 +119,8 @@ def load_library():
         "tfhe_b200_set_tuning": (i32, [vp, C.c_char_p, i32]),
         "tfhe_b200_measure_fp64_tflops": (C.c_double, [vp, i32]),
         "tfhe_b200_last_kernel_ms": (C.c_double, [vp, i32, i32]),
+        "tfhe_b200_lut_bootstrap_batch": (i32, [vp, vp, vp, sz, vp, i32, i32]),
+        "tfhe_b200_lut_generate": (i32, [vp, vp, i32, vp]),
         "tfhe_b200_circuit_create": (i32, [vp, vp, sz, sz, vp, sz, vp]),
         "tfhe_b200_circuit_destroy": (None, [vp]),
         "tfhe_b200_circuit_info": (i32, [vp, vp, vp, vp]),
@@ -141,6 +143,7 @@ EXPORTED_SYMBOLS = [
     "tfhe_b200_stream", "tfhe_b200_sync", "tfhe_b200_track_margin", "tfhe_b200_max_round_margin", "tfhe_b200_launch_count",
     "tfhe_b200_set_tuning", "tfhe_b200_measure_fp64_tflops", "tfhe_b200_last_kernel_ms",
     "tfhe_b200_load_reencryption_key", "tfhe_b200_reencrypt_batch",
+    "tfhe_b200_lut_bootstrap_batch", "tfhe_b200_lut_generate",
     "tfhe_b200_circuit_create", "tfhe_b200_circuit_destroy", "tfhe_b200_circuit_info", "tfhe_b200_circuit_run",
 ]
 
@@ -250,6 +253,23 @@ class Context:
         out = np.empty((B, w), np.uint32)
         tv = _u32(testvec) if testvec is not None else None
         self._check(self.lib.tfhe_b200_bootstrap_batch(self.h, _ptr(ct), _ptr(out), B, _ptr(tv), 1 if tv_per_item else 0))
+        return out
+
+    def lut_bootstrap_batch(self, ct, tables, per_item=False):
+        """tables: torus values [B][m] (per_item) or [m]; test vectors are generated on the device"""
+        w = self.n + 1
+        ct = _u32(ct, w); B = ct.shape[0]
+        tables = np.ascontiguousarray(tables, dtype=np.uint32)
+        m = tables.shape[-1]
+        assert tables.shape == ((B, m) if per_item else (m,)), tables.shape
+        out = np.empty((B, w), np.uint32)
+        self._check(self.lib.tfhe_b200_lut_bootstrap_batch(self.h, _ptr(ct), _ptr(out), B, _ptr(tables), m, 1 if per_item else 0))
+        return out
+
+    def lut_generate(self, table):
+        table = np.ascontiguousarray(table, dtype=np.uint32)
+        out = np.empty((2, 1024), np.uint32)
+        self._check(self.lib.tfhe_b200_lut_generate(self.h, _ptr(table), table.shape[0], _ptr(out)))
         return out
 
     def bootstrap_no_keyswitch_batch(self, ct):

@@ -43,6 +43,9 @@ pub extern fn tfhe_b200_set_mode(ctx: *Ctx, mode: c_int) c_int;
 pub extern fn tfhe_b200_gate_batch(ctx: *Ctx, op: c_int, a: [*]const u32, b: [*]const u32, out: [*]u32, count: usize) c_int;
 pub extern fn tfhe_b200_gate_batch_ops(ctx: *Ctx, ops: [*]const i32, a: [*]const u32, b: [*]const u32, out: [*]u32, count: usize) c_int;
 pub extern fn tfhe_b200_bootstrap_batch(ctx: *Ctx, in: [*]const u32, out: [*]u32, count: usize, testvec: ?[*]const u32, tv_per_item: c_int) c_int;
+/// programmable bootstrap from function tables [count][message_modulus] (or one shared table): lut.Generator runs on the device
+pub extern fn tfhe_b200_lut_bootstrap_batch(ctx: *Ctx, in: [*]const u32, out: [*]u32, count: usize, tables: [*]const u32, message_modulus: c_int, per_item: c_int) c_int;
+pub extern fn tfhe_b200_lut_generate(ctx: *Ctx, table: [*]const u32, message_modulus: c_int, testvec_out: [*]u32) c_int;
 pub extern fn tfhe_b200_bootstrap_no_keyswitch_batch(ctx: *Ctx, in: [*]const u32, out: [*]u32, count: usize) c_int;
 pub extern fn tfhe_b200_blind_rotate_batch(ctx: *Ctx, in: [*]const u32, trlwe_out: [*]u32, count: usize, testvec: ?[*]const u32, tv_per_item: c_int) c_int;
 pub extern fn tfhe_b200_keyswitch_batch(ctx: *Ctx, lv1: [*]const u32, lv0: [*]u32, count: usize) c_int;
