@@ -99,6 +99,17 @@ int tfhe_b200_load_key(tfhe_b200_ctx *ctx, const double *bsk, const uint32_t *ks
  * layouts as above, KSK rows packed ((n+1)*4 bytes). */
 int tfhe_b200_load_key_device(tfhe_b200_ctx *ctx, int dev, const double *d_bsk, const uint32_t *d_ksk,
                               uint32_t decomposition_offset);
+/* key.CloudKey.new (src/key.zig:70-77): genKeySwitchingKey + genBootstrappingKey (src/key.zig:148-212) ON THE DEVICE, from
+ * the secret key the caller holds (key_lv0: uint32_t[n], key_lv1: uint32_t[N], entries 0/1 as in key.SecretKey,
+ * src/key.zig:23-58).  ksk_alpha / bsk_alpha = params.KSK_ALPHA / BSK_ALPHA (src/params.zig:419-422).
+ * Randomness: Philox4x32-10 keyed by `seed` (the reference's own seeding is a clock, src/utils.zig:16-22), so every
+ * device of the context generates the identical key and a key is reproducible from its seed.  The keys are written
+ * straight into the device layouts; bsk_out / ksk_out (either may be NULL) receive the reference layouts described
+ * at the top of this file, e.g. to hand the same CloudKey to the CPU implementation or to serialise it. */
+int tfhe_b200_keygen(tfhe_b200_ctx *ctx, const uint32_t *key_lv0, const uint32_t *key_lv1, uint64_t seed, double ksk_alpha,
+                     double bsk_alpha, double *bsk_out, uint32_t *ksk_out);
+/* CloudKey.decomposition_offset of the loaded / generated key (key.genDecompositionOffset, src/key.zig:121-131) */
+uint32_t tfhe_b200_decomposition_offset(const tfhe_b200_ctx *ctx);
 int tfhe_b200_set_mode(tfhe_b200_ctx *ctx, int mode);
 
 /* ---- hot path, host buffers ---------------------------------------------------------- */

@@ -445,6 +445,52 @@ int tfhe_b200_load_key_device(tfhe_b200_ctx *c, int dev, const double *d_bsk, co
     return 0;
 }
 
+
+int tfhe_b200_keygen(tfhe_b200_ctx *c, const uint32_t *key_lv0, const uint32_t *key_lv1, uint64_t seed, double ksk_alpha, double bsk_alpha,
+                     double *bsk_out, uint32_t *ksk_out) {
+    if (!c || !key_lv0 || !key_lv1 || !(ksk_alpha >= 0.0) || !(bsk_alpha >= 0.0)) return fail(c, TFHE_B200_ERR_INVALID, "bad keygen argument");
+    const tfhe_b200_params &p = c->prm;
+    const int base = 1 << p.basebit;
+    const size_t bsk_doubles = (size_t)p.n * 2 * p.L * 2 * kN;
+    const size_t ksk_ref_words = (size_t)kN * p.iks_t * base * (p.n + 1);
+    for (size_t k = 0; k < c->devs.size(); k++) {
+        Device &d = c->devs[k];
+        CU(c, cudaSetDevice(d.id));
+        uint32_t *d_s0 = nullptr, *d_s1 = nullptr, *d_kref = nullptr;
+        CU(c, cudaMalloc(&d_s0, (size_t)p.n * 4));
+        CU(c, cudaMalloc(&d_s1, (size_t)kN * 4));
+        CU(c, cudaMemcpyAsync(d_s0, key_lv0, (size_t)p.n * 4, cudaMemcpyHostToDevice, d.stream));
+        CU(c, cudaMemcpyAsync(d_s1, key_lv1, (size_t)kN * 4, cudaMemcpyHostToDevice, d.stream));
+        if (d.bsk) CU(c, cudaFree(d.bsk));
+        if (d.bsk_ref) CU(c, cudaFree(d.bsk_ref));
+        if (d.ksk) CU(c, cudaFree(d.ksk));
+        d.bsk = nullptr; d.bsk_ref = nullptr; d.ksk = nullptr;
+        CU(c, cudaMalloc(&d.bsk, bsk_doubles * 8));
+        CU(c, cudaMalloc(&d.bsk_ref, bsk_doubles * 8));
+        CU(c, cudaMalloc(&d.ksk, (size_t)kN * p.iks_t * (base - 1) * c->ksk_pitch * 4));
+        if (k == 0 && ksk_out) {     // reference layout incl. the never-read k = 0 rows (zeroed here; uninitialised upstream)
+            CU(c, cudaMalloc(&d_kref, ksk_ref_words * 4));
+            CU(c, cudaMemsetAsync(d_kref, 0, ksk_ref_words * 4, d.stream));
+        }
+        CU(c, launch_keygen_bsk(d_s0, d_s1, seed, bsk_alpha, p.n, p.L, p.bgbit, d.tw2, d.tw3, d.bsk, d.bsk_ref, d.stream, &c->launches));
+        CU(c, launch_keygen_ksk(d_s0, d_s1, seed, ksk_alpha, p.n, p.basebit, p.iks_t, c->ksk_pitch, d.ksk, d_kref, d.stream, &c->launches));
+        if (k == 0 && bsk_out) CU(c, cudaMemcpyAsync(bsk_out, d.bsk_ref, bsk_doubles * 8, cudaMemcpyDeviceToHost, d.stream));
+        if (d_kref) CU(c, cudaMemcpyAsync(ksk_out, d_kref, ksk_ref_words * 4, cudaMemcpyDeviceToHost, d.stream));
+        CU(c, cudaStreamSynchronize(d.stream));
+        CU(c, cudaFree(d_s0));
+        CU(c, cudaFree(d_s1));
+        if (d_kref) CU(c, cudaFree(d_kref));
+    }
+    uint32_t offset = 0;             // key.genDecompositionOffset (src/key.zig:121-131)
+    for (int i = 0; i < p.L; i++) offset += (1u << (p.bgbit - 1)) << (32 - (i + 1) * p.bgbit);
+    c->offset = offset;
+    c->has_key = true;
+    c->has_ksk = true;
+    return 0;
+}
+
+uint32_t tfhe_b200_decomposition_offset(const tfhe_b200_ctx *c) { return c ? c->offset : 0u; }
+
 int tfhe_b200_set_mode(tfhe_b200_ctx *c, int mode) {
     if (!c || (mode != TFHE_B200_MODE_FAST && mode != TFHE_B200_MODE_EXACT)) return fail(c, TFHE_B200_ERR_INVALID, "bad mode");
     c->mode = mode;

@@ -64,6 +64,11 @@ cudaError_t launch_repack_ksk(const uint32_t *ref_ksk, size_t ref_row_stride_u32
                               int pitch, int in_dim, cudaStream_t s, uint64_t *launches);
 // test vectors [count][2][N] from function tables [count][m] of torus values (lut/generator.zig:158-191)
 cudaError_t launch_build_testvec(const uint32_t *tables, int m, uint32_t *out, size_t count, cudaStream_t s, uint64_t *launches);
+// cloud-key generation on the device (keygen.cu): key.genKeySwitchingKey / genBootstrappingKey (src/key.zig:148-212)
+cudaError_t launch_keygen_ksk(const uint32_t *s0, const uint32_t *s1, uint64_t seed, double alpha, int n, int basebit, int iks_t, int pitch,
+                              uint32_t *dev, uint32_t *ref, cudaStream_t s, uint64_t *launches);
+cudaError_t launch_keygen_bsk(const uint32_t *s0, const uint32_t *s1, uint64_t seed, double alpha, int n, int L, int bgbit, const cplx *tw2,
+                              const cplx *tw3, cplx *dev, double *ref, cudaStream_t s, uint64_t *launches);
 // K3: out = -a over [B][n+1]
 cudaError_t launch_negate(const uint32_t *a, uint32_t *out, size_t count, cudaStream_t s, uint64_t *launches);
 // first n entries + body of an lv1 sample -> TLWELv0-shaped "hybrid" sample (trlwe.zig:165-180)

@@ -119,6 +119,8 @@ def load_library():
         "tfhe_b200_set_tuning": (i32, [vp, C.c_char_p, i32]),
         "tfhe_b200_measure_fp64_tflops": (C.c_double, [vp, i32]),
         "tfhe_b200_last_kernel_ms": (C.c_double, [vp, i32, i32]),
+        "tfhe_b200_keygen": (i32, [vp, vp, vp, C.c_uint64, C.c_double, C.c_double, vp, vp]),
+        "tfhe_b200_decomposition_offset": (u32, [vp]),
         "tfhe_b200_lut_bootstrap_batch": (i32, [vp, vp, vp, sz, vp, i32, i32]),
         "tfhe_b200_lut_generate": (i32, [vp, vp, i32, vp]),
         "tfhe_b200_circuit_create": (i32, [vp, vp, sz, sz, vp, sz, vp]),
@@ -143,7 +145,7 @@ EXPORTED_SYMBOLS = [
     "tfhe_b200_stream", "tfhe_b200_sync", "tfhe_b200_track_margin", "tfhe_b200_max_round_margin", "tfhe_b200_launch_count",
     "tfhe_b200_set_tuning", "tfhe_b200_measure_fp64_tflops", "tfhe_b200_last_kernel_ms",
     "tfhe_b200_load_reencryption_key", "tfhe_b200_reencrypt_batch",
-    "tfhe_b200_lut_bootstrap_batch", "tfhe_b200_lut_generate",
+    "tfhe_b200_keygen", "tfhe_b200_decomposition_offset", "tfhe_b200_lut_bootstrap_batch", "tfhe_b200_lut_generate",
     "tfhe_b200_circuit_create", "tfhe_b200_circuit_destroy", "tfhe_b200_circuit_info", "tfhe_b200_circuit_run",
 ]
 
@@ -221,6 +223,18 @@ class Context:
 
     def load_cloud_key(self, ck: CloudKey):
         self.load_key(ck.bootstrapping_key, ck.key_switching_key, ck.decomposition_offset)
+
+    def keygen(self, key_lv0, key_lv1, seed: int, ksk_alpha: float, bsk_alpha: float, export: bool = True):
+        """Generate the cloud key on the device(s) from a host-held secret key (key.CloudKey.new, key.zig:70-77).
+        Returns a CloudKey in the reference layouts when `export`, else None."""
+        s0 = _u32(key_lv0); s1 = _u32(key_lv1)
+        assert s0.shape == (self.n,) and s1.shape == (1024,)
+        p = self.params
+        bsk = np.empty((p.n, 2 * p.L, 2, 1024), np.float64) if export else None
+        ksk = np.empty((1024 * p.iks_t * (1 << p.basebit), p.n + 1), np.uint32) if export else None
+        self._check(self.lib.tfhe_b200_keygen(self.h, _ptr(s0), _ptr(s1), int(seed) & 0xFFFFFFFFFFFFFFFF, float(ksk_alpha), float(bsk_alpha),
+                                              _ptr(bsk), _ptr(ksk)))
+        return CloudKey(bsk, ksk, int(self.lib.tfhe_b200_decomposition_offset(self.h))) if export else None
 
     def load_key_device(self, dev: int, d_bsk: int, d_ksk: int | None, offset: int):
         self._check(self.lib.tfhe_b200_load_key_device(self.h, dev, _ptr(d_bsk), _ptr(d_ksk), int(offset) & 0xFFFFFFFF))

@@ -39,6 +39,9 @@ pub extern fn tfhe_b200_destroy(ctx: ?*Ctx) void;
 pub extern fn tfhe_b200_last_error(ctx: ?*const Ctx) [*:0]const u8;
 pub extern fn tfhe_b200_num_devices(ctx: ?*const Ctx) c_int;
 pub extern fn tfhe_b200_load_key(ctx: *Ctx, bsk: [*]const f64, ksk: ?[*]const u32, ksk_row_stride_bytes: usize, decomposition_offset: u32) c_int;
+/// key.CloudKey.new on the device from the host-held secret key (key_lv0: [n]u32, key_lv1: [N]u32); bsk_out / ksk_out optional
+pub extern fn tfhe_b200_keygen(ctx: *Ctx, key_lv0: [*]const u32, key_lv1: [*]const u32, seed: u64, ksk_alpha: f64, bsk_alpha: f64, bsk_out: ?[*]f64, ksk_out: ?[*]u32) c_int;
+pub extern fn tfhe_b200_decomposition_offset(ctx: *const Ctx) u32;
 pub extern fn tfhe_b200_set_mode(ctx: *Ctx, mode: c_int) c_int;
 pub extern fn tfhe_b200_gate_batch(ctx: *Ctx, op: c_int, a: [*]const u32, b: [*]const u32, out: [*]u32, count: usize) c_int;
 pub extern fn tfhe_b200_gate_batch_ops(ctx: *Ctx, ops: [*]const i32, a: [*]const u32, b: [*]const u32, out: [*]u32, count: usize) c_int;
