@@ -8,7 +8,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/tfhe_b200.h"
@@ -38,6 +40,7 @@ struct Device {
     Buf a, b, out, lv1, ops, tv, trlwe, lut;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // K1 start, K1 end / K2 start, K2 end (timing mode)
     bool ev_valid = false;
+    uint64_t launches = 0;             // kernels launched on this device by its host thread (summed by tfhe_b200_launch_count)
 };
 
 }  // namespace
@@ -46,6 +49,7 @@ struct tfhe_b200_ctx {
     tfhe_b200_params prm{};
     std::vector<Device> devs;
     std::string err;
+    std::mutex err_mu;                 // the per-device host threads of a multi-device batch may fail concurrently
     int mode = TFHE_B200_MODE_FAST;
     bool track_margin = false;
     bool has_key = false, has_ksk = false, has_reenc = false;
@@ -69,7 +73,10 @@ int fail(tfhe_b200_ctx *c, int code, const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(buf, sizeof(buf), fmt, ap);
     va_end(ap);
-    if (c) c->err = buf;
+    if (c) {
+        std::lock_guard<std::mutex> lk(c->err_mu);
+        c->err = buf;
+    }
     return code;
 }
 
@@ -126,18 +133,18 @@ int run_device(tfhe_b200_ctx *c, Device &d, int op, const int32_t *d_ops, const 
     d.ev_valid = false;
     if (c->timing) CU(c, cudaEventRecord(d.ev[0], d.stream));
     if (c->mode == TFHE_B200_MODE_EXACT) {
-        CU(c, launch_blind_rotate_exact(A, d.exact_tables, d.bsk_ref, c->track_margin, d.stream, &c->launches));
+        CU(c, launch_blind_rotate_exact(A, d.exact_tables, d.bsk_ref, c->track_margin, d.stream, &d.launches));
     } else {
         BrTuning tune = c->tune;
         tune.sm_count = d.sm_count;
         tune.concurrent = concurrent ? 1 : 0;
-        CU(c, launch_blind_rotate(A, tune, c->track_margin, d.stream, &c->launches));
+        CU(c, launch_blind_rotate(A, tune, c->track_margin, d.stream, &d.launches));
     }
     if (c->timing) CU(c, cudaEventRecord(d.ev[1], d.stream));
     if (d_lv0) {
         if (!c->has_ksk) return fail(c, TFHE_B200_ERR_NO_KEY, "no key-switching key loaded");
         KsArgs K{lv1, d_lv0, d.ksk, (uint32_t)B, c->prm.n, c->prm.basebit, c->prm.iks_t, c->ksk_pitch, kN, c->ks_tile, c->ks_vec};
-        CU(c, launch_keyswitch(K, d.sm_count, d.stream, &c->launches));
+        CU(c, launch_keyswitch(K, d.sm_count, d.stream, &d.launches));
     }
     if (c->timing) {
         CU(c, cudaEventRecord(d.ev[2], d.stream));
@@ -148,91 +155,84 @@ int run_device(tfhe_b200_ctx *c, Device &d, int op, const int32_t *d_ops, const 
 
 enum class Out { LV0, LV0_NOKS, LV1, TRLWE };
 
-// host-buffer driver: shard contiguously over devices, chunk, stage, launch, copy back
+// host-buffer driver: shard contiguously over devices; every device is driven by its own host thread (chunk, stage,
+// launch, copy back), the stand-in for the reference's CPU thread pool (src/parallel/thread_pool.zig:39-83).  Copies
+// from pageable host memory block the issuing thread, so one thread per device is what lets the H2D / D2H traffic of
+// all devices (each on its own PCIe link) and their kernels proceed concurrently.
+int run_host_device(tfhe_b200_ctx *c, Device &d, size_t lo, size_t hi, int op, const int32_t *ops, const uint32_t *a, const uint32_t *b,
+                    void *out, Out kind, const uint32_t *tv, int tv_per_item, int lut_m) {
+    const size_t w0 = (size_t)c->prm.n + 1, w1 = (size_t)kN + 1, wt = (size_t)2 * kN;
+    const size_t wout = (kind == Out::LV0 || kind == Out::LV0_NOKS) ? w0 : (kind == Out::LV1) ? w1 : wt;
+    const bool two_inputs = (op >= 0 || ops);
+    for (size_t off = lo; off < hi; off += c->max_chunk) {
+        const size_t nb = std::min(c->max_chunk, hi - off);
+        CU(c, cudaSetDevice(d.id));
+        if (int r = ensure(c, d.a, nb * w0 * 4)) return r;
+        CU(c, cudaMemcpyAsync(d.a.p, a + off * w0, nb * w0 * 4, cudaMemcpyHostToDevice, d.stream));
+        if (two_inputs) {
+            if (int r = ensure(c, d.b, nb * w0 * 4)) return r;
+            CU(c, cudaMemcpyAsync(d.b.p, b + off * w0, nb * w0 * 4, cudaMemcpyHostToDevice, d.stream));
+        }
+        const int32_t *d_ops = nullptr;
+        if (ops) {
+            if (int r = ensure(c, d.ops, nb * 4)) return r;
+            CU(c, cudaMemcpyAsync(d.ops.p, ops + off, nb * 4, cudaMemcpyHostToDevice, d.stream));
+            d_ops = (const int32_t *)d.ops.p;
+        }
+        const uint32_t *d_tv = nullptr;
+        if (tv && lut_m > 0) {   // function tables in, test vectors built on the device
+            const size_t cnt = tv_per_item ? nb : 1;
+            if (int r = ensure(c, d.tv, cnt * wt * 4)) return r;
+            if (int r = ensure(c, d.lut, cnt * lut_m * 4)) return r;
+            CU(c, cudaMemcpyAsync(d.lut.p, tv + (tv_per_item ? off * lut_m : 0), cnt * lut_m * 4, cudaMemcpyHostToDevice, d.stream));
+            CU(c, launch_build_testvec((const uint32_t *)d.lut.p, lut_m, (uint32_t *)d.tv.p, cnt, d.stream, &d.launches));
+            d_tv = (const uint32_t *)d.tv.p;
+        } else if (tv) {
+            const size_t tvb = (tv_per_item ? nb : 1) * wt * 4;
+            if (int r = ensure(c, d.tv, tvb)) return r;
+            CU(c, cudaMemcpyAsync(d.tv.p, tv + (tv_per_item ? off * wt : 0), tvb, cudaMemcpyHostToDevice, d.stream));
+            d_tv = (const uint32_t *)d.tv.p;
+        }
+        if (int r = ensure(c, d.out, nb * wout * 4)) return r;
+        uint32_t *d_out = (uint32_t *)d.out.p;
+        int r = 0;
+        if (kind == Out::LV0)
+            r = run_device(c, d, ops ? 0 : op, d_ops, (uint32_t *)d.a.p, (uint32_t *)d.b.p, d_out, nullptr, nullptr, nb, d_tv, tv_per_item);
+        else if (kind == Out::LV1)
+            r = run_device(c, d, ops ? 0 : op, d_ops, (uint32_t *)d.a.p, (uint32_t *)d.b.p, nullptr, d_out, nullptr, nb, d_tv, tv_per_item);
+        else if (kind == Out::TRLWE)
+            r = run_device(c, d, ops ? 0 : op, d_ops, (uint32_t *)d.a.p, (uint32_t *)d.b.p, nullptr, nullptr, d_out, nb, d_tv, tv_per_item);
+        else {  // LV0_NOKS: blind rotate + extract, then keep the first n mask entries + body
+            if (int r2 = ensure(c, d.lv1, nb * w1 * 4)) return r2;
+            r = run_device(c, d, ops ? 0 : op, d_ops, (uint32_t *)d.a.p, (uint32_t *)d.b.p, nullptr, (uint32_t *)d.lv1.p, nullptr, nb, d_tv,
+                           tv_per_item);
+            if (!r) CU(c, launch_extract2((uint32_t *)d.lv1.p, d_out, (uint32_t)nb, c->prm.n, d.stream, &d.launches));
+        }
+        if (r) return r;
+        CU(c, cudaMemcpyAsync((uint32_t *)out + off * wout, d.out.p, nb * wout * 4, cudaMemcpyDeviceToHost, d.stream));
+        CU(c, cudaStreamSynchronize(d.stream));
+    }
+    return 0;
+}
+
 int run_host(tfhe_b200_ctx *c, int op, const int32_t *ops, const uint32_t *a, const uint32_t *b, void *out, Out kind, size_t B,
              const uint32_t *tv, int tv_per_item, int lut_m = 0) {   // lut_m > 0: `tv` holds function tables [B or 1][lut_m]
     if (!c) return TFHE_B200_ERR_INVALID;
     if (!c->has_key) return fail(c, TFHE_B200_ERR_NO_KEY, "no cloud key loaded");
     if (B == 0) return 0;
     if (!a || !out || ((op >= 0 || ops) && !b)) return fail(c, TFHE_B200_ERR_INVALID, "null buffer");
-    const size_t w0 = (size_t)c->prm.n + 1, w1 = (size_t)kN + 1, wt = (size_t)2 * kN;
-    const size_t wout = (kind == Out::LV0 || kind == Out::LV0_NOKS) ? w0 : (kind == Out::LV1) ? w1 : wt;
     const int nd = (int)c->devs.size();
-    const bool two_inputs = (op >= 0 || ops);
-    // all devices proceed chunk-round by chunk-round; within a round work is asynchronous per device
-    std::vector<size_t> lo(nd), hi(nd), pos(nd);
-    for (int k = 0; k < nd; k++) { lo[k] = B * k / nd; hi[k] = B * (k + 1) / nd; pos[k] = lo[k]; }
-    std::vector<size_t> round_off(nd), round_nb(nd);
-    bool more = true;
-    while (more) {
-        more = false;
-        for (int k = 0; k < nd; k++) {
-            Device &d = c->devs[k];
-            const size_t nb = std::min(c->max_chunk, hi[k] - pos[k]);
-            round_nb[k] = 0;
-            if (nb == 0) continue;
-            const size_t off = pos[k];
-            CU(c, cudaSetDevice(d.id));
-            if (int r = ensure(c, d.a, nb * w0 * 4)) return r;
-            CU(c, cudaMemcpyAsync(d.a.p, a + off * w0, nb * w0 * 4, cudaMemcpyHostToDevice, d.stream));
-            if (two_inputs) {
-                if (int r = ensure(c, d.b, nb * w0 * 4)) return r;
-                CU(c, cudaMemcpyAsync(d.b.p, b + off * w0, nb * w0 * 4, cudaMemcpyHostToDevice, d.stream));
-            }
-            const int32_t *d_ops = nullptr;
-            if (ops) {
-                if (int r = ensure(c, d.ops, nb * 4)) return r;
-                CU(c, cudaMemcpyAsync(d.ops.p, ops + off, nb * 4, cudaMemcpyHostToDevice, d.stream));
-                d_ops = (const int32_t *)d.ops.p;
-            }
-            const uint32_t *d_tv = nullptr;
-            if (tv && lut_m > 0) {   // function tables in, test vectors built on the device
-                const size_t cnt = tv_per_item ? nb : 1;
-                if (int r = ensure(c, d.tv, cnt * wt * 4)) return r;
-                if (int r = ensure(c, d.lut, cnt * lut_m * 4)) return r;
-                CU(c, cudaMemcpyAsync(d.lut.p, tv + (tv_per_item ? off * lut_m : 0), cnt * lut_m * 4, cudaMemcpyHostToDevice, d.stream));
-                CU(c, launch_build_testvec((const uint32_t *)d.lut.p, lut_m, (uint32_t *)d.tv.p, cnt, d.stream, &c->launches));
-                d_tv = (const uint32_t *)d.tv.p;
-            } else if (tv) {
-                const size_t tvb = (tv_per_item ? nb : 1) * wt * 4;
-                if (int r = ensure(c, d.tv, tvb)) return r;
-                CU(c, cudaMemcpyAsync(d.tv.p, tv + (tv_per_item ? off * wt : 0), tvb, cudaMemcpyHostToDevice, d.stream));
-                d_tv = (const uint32_t *)d.tv.p;
-            }
-            if (int r = ensure(c, d.out, nb * wout * 4)) return r;
-            uint32_t *d_out = (uint32_t *)d.out.p;
-            int r = 0;
-            if (kind == Out::LV0)
-                r = run_device(c, d, ops ? 0 : op, d_ops, (uint32_t *)d.a.p, (uint32_t *)d.b.p, d_out, nullptr, nullptr, nb, d_tv, tv_per_item);
-            else if (kind == Out::LV1)
-                r = run_device(c, d, ops ? 0 : op, d_ops, (uint32_t *)d.a.p, (uint32_t *)d.b.p, nullptr, d_out, nullptr, nb, d_tv, tv_per_item);
-            else if (kind == Out::TRLWE)
-                r = run_device(c, d, ops ? 0 : op, d_ops, (uint32_t *)d.a.p, (uint32_t *)d.b.p, nullptr, nullptr, d_out, nb, d_tv, tv_per_item);
-            else {  // LV0_NOKS: blind rotate + extract, then keep the first n mask entries + body
-                if (int r2 = ensure(c, d.lv1, nb * w1 * 4)) return r2;
-                r = run_device(c, d, ops ? 0 : op, d_ops, (uint32_t *)d.a.p, (uint32_t *)d.b.p, nullptr, (uint32_t *)d.lv1.p, nullptr, nb, d_tv,
-                               tv_per_item);
-                if (!r) CU(c, launch_extract2((uint32_t *)d.lv1.p, d_out, (uint32_t)nb, c->prm.n, d.stream, &c->launches));
-            }
-            if (r) return r;
-            round_off[k] = off;
-            round_nb[k] = nb;
-            pos[k] += nb;
-            if (pos[k] < hi[k]) more = true;
-        }
-        // second phase: copy back.  A D2H copy into pageable memory blocks the host until that device is done, so it
-        // is issued only after EVERY device has its kernels in flight (the devices run concurrently).
-        for (int k = 0; k < nd; k++) {
-            if (round_nb[k] == 0) continue;
-            Device &d = c->devs[k];
-            CU(c, cudaSetDevice(d.id));
-            CU(c, cudaMemcpyAsync((uint32_t *)out + round_off[k] * wout, d.out.p, round_nb[k] * wout * 4, cudaMemcpyDeviceToHost, d.stream));
-        }
-        for (int k = 0; k < nd; k++) {
-            CU(c, cudaSetDevice(c->devs[k].id));
-            CU(c, cudaStreamSynchronize(c->devs[k].stream));
-        }
+    if (nd == 1) return run_host_device(c, c->devs[0], 0, B, op, ops, a, b, out, kind, tv, tv_per_item, lut_m);
+    std::vector<int> rc(nd, 0);
+    std::vector<std::thread> workers;
+    for (int k = 0; k < nd; k++) {
+        const size_t lo = B * k / nd, hi = B * (k + 1) / nd;
+        if (lo == hi) continue;
+        workers.emplace_back([=, &rc] { rc[k] = run_host_device(c, c->devs[k], lo, hi, op, ops, a, b, out, kind, tv, tv_per_item, lut_m); });
     }
+    for (auto &w : workers) w.join();
+    for (int k = 0; k < nd; k++)
+        if (rc[k]) return rc[k];
     return 0;
 }
 
@@ -317,13 +317,15 @@ int circuit_levels(tfhe_b200_ctx *c, tfhe_b200_circuit *q, Device &dev, tfhe_b20
     uint32_t *wires = (uint32_t *)pd.wires.p;
     Device d = dev;              // same keys and tables, this lane's stream
     d.stream = pd.stream;
+    int rc = 0;
     for (const auto &lv : q->levels) {
         LevelRef ref{pd.d_ops + lv.off, pd.d_a + lv.off, pd.d_b + lv.off, (uint32_t)inst};
-        if (int r = run_device(c, d, 0, nullptr, wires, nullptr, wires + (size_t)lv.first_slot * inst * w0, (uint32_t *)pd.lv1.p, nullptr,
-                               (size_t)lv.G * inst, nullptr, 0, &ref, q->lanes > 1))
-            return r;
+        rc = run_device(c, d, 0, nullptr, wires, nullptr, wires + (size_t)lv.first_slot * inst * w0, (uint32_t *)pd.lv1.p, nullptr,
+                        (size_t)lv.G * inst, nullptr, 0, &ref, q->lanes > 1);
+        if (rc) break;
     }
-    return 0;
+    dev.launches = d.launches;   // the copy counted them
+    return rc;
 }
 
 // enqueue every level of the circuit for `inst` instances whose input wires are already in pd.wires
@@ -331,15 +333,15 @@ int circuit_enqueue(tfhe_b200_ctx *c, tfhe_b200_circuit *q, Device &d, tfhe_b200
     if (!c->circuit_graph || c->timing || pd.graph_failed) return circuit_levels(c, q, d, pd, inst);
     if (!pd.graph || pd.graph_inst != inst) {
         if (pd.graph) { cudaGraphExecDestroy(pd.graph); pd.graph = nullptr; }
-        const uint64_t before = c->launches;
+        const uint64_t before = d.launches;
         cudaGraph_t g = nullptr;
         bool ok = cudaStreamBeginCapture(pd.stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
         int r = ok ? circuit_levels(c, q, d, pd, inst) : 0;
         if (ok) ok = cudaStreamEndCapture(pd.stream, &g) == cudaSuccess && r == 0 && g != nullptr;
         if (ok) ok = cudaGraphInstantiate(&pd.graph, g, 0) == cudaSuccess;
         if (g) cudaGraphDestroy(g);
-        pd.graph_launches = c->launches - before;
-        c->launches = before;
+        pd.graph_launches = d.launches - before;
+        d.launches = before;
         if (!ok) {               // capture refused: run the levels eagerly from now on
             cudaGetLastError();
             pd.graph = nullptr;
@@ -349,7 +351,7 @@ int circuit_enqueue(tfhe_b200_ctx *c, tfhe_b200_circuit *q, Device &d, tfhe_b200
         pd.graph_inst = inst;
     }
     CU(c, cudaGraphLaunch(pd.graph, pd.stream));
-    c->launches += pd.graph_launches;
+    d.launches += pd.graph_launches;
     return 0;
 }
 
@@ -854,7 +856,12 @@ double tfhe_b200_max_round_margin(tfhe_b200_ctx *c, int reset) {
     return m;
 }
 
-uint64_t tfhe_b200_launch_count(const tfhe_b200_ctx *c) { return c ? c->launches : 0; }
+uint64_t tfhe_b200_launch_count(const tfhe_b200_ctx *c) {
+    if (!c) return 0;
+    uint64_t n = c->launches;
+    for (const Device &d : c->devs) n += d.launches;
+    return n;
+}
 
 int tfhe_b200_set_tuning(tfhe_b200_ctx *c, const char *key, int value) {
     if (!c || !key) return TFHE_B200_ERR_INVALID;
