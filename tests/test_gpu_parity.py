@@ -209,15 +209,24 @@ def test_chunked_launches_equal_single_launch(ctx128, orc128, keys128):
 
 
 def test_latency_mode_equals_throughput_mode(ctx128, orc128, keys128):
-    """batches <= SM count run one CTA per ciphertext with the 2L transforms in parallel; same bits"""
-    a, b, ca, cb = _enc_pairs(orc128, keys128, 40, seed=14)
-    lat = ctx128.gate_batch(O.XOR, ca, cb)
-    ctx128.set_tuning("latency_mode", 0)
+    """batches <= SM count / 2 run one two-CTA cluster per ciphertext (each CTA owns one accumulator half, partial sums
+    cross through distributed shared memory), batches <= SM count one CTA per ciphertext with the 2L transforms in
+    parallel; same bits as the throughput kernel"""
+    a, b, ca, cb = _enc_pairs(orc128, keys128, 100, seed=14)
+    pair = ctx128.gate_batch(O.XOR, ca[:40], cb[:40])        # 40 <= 74: cluster kernel
+    lat = ctx128.gate_batch(O.XOR, ca, cb)                   # 74 < 100 <= 148: single-CTA latency kernel
+    ctx128.set_tuning("latency_mode", 2)
     try:
+        lat40 = ctx128.gate_batch(O.XOR, ca[:40], cb[:40])   # single-CTA latency kernel forced
+        ctx128.set_tuning("latency_mode", 0)
         thr = ctx128.gate_batch(O.XOR, ca, cb)
     finally:
         ctx128.set_tuning("latency_mode", 1)
-    assert (lat == thr).all()
+    assert (lat == thr).all() and (pair == thr[:40]).all() and (lat40 == thr[:40]).all()
+    one = ctx128.gate_batch(O.XOR, ca[:1], cb[:1])
+    assert (one == thr[:1]).all()
+    tr = ctx128.blind_rotate_batch(np.stack([orc128.gate_linear(O.NAND, ca[i], cb[i]) for i in range(5)]))   # TRLWE output path of the pair kernel
+    assert (tr == orc128.blind_rotate_batch(np.stack([orc128.gate_linear(O.NAND, ca[i], cb[i]) for i in range(5)]), keys128)).all()
     assert (lat[:6] == orc128.gate_batch(O.XOR, ca[:6], cb[:6], keys128)).all()
     ctx128.track_margin(True)
     try:

@@ -22,9 +22,9 @@ d_a = torch.from_numpy(HK.encrypt_bools(a, params, sk, rng).view(np.int32)).cuda
 d_b = torch.from_numpy(HK.encrypt_bools(b, params, sk, rng).view(np.int32)).cuda()
 d_o = torch.empty_like(d_a)
 stream = torch.cuda.ExternalStream(ctx.stream(0))
-for mode in (1, 0):
+for mode in (1, 2, 0):
     ctx.set_tuning("latency_mode", mode)
-    for B in (1, 16, 148, 296, 592, 2048):
+    for B in (1, 16, 74, 148, 296, 592, 2048):
         ts = []
         for _ in range(12):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

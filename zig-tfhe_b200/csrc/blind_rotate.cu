@@ -620,6 +620,187 @@ __global__ void __launch_bounds__(2 * L * kGroupThreads, 1) blind_rotate_latency
 // exposed latency is that of the loads themselves, not of the barrier; see DESIGN.md section 4 and
 // profiles/r01_team_probe.log.  The code was removed again.)
 
+// ---------------------------------------------------------------------------------------------------
+// Latency mode on a pair of SMs (batches of at most sm_count / 2 ciphertexts): a thread-block cluster of two CTAs per
+// ciphertext.  CTA h owns polynomial h of the accumulator (h = 0: a, 1: b): its L groups of 64 threads transform the L
+// digit polynomials of that half concurrently and multiply them with their key rows (both output parts); the L
+// products per output are summed inside the CTA; the partial sum for the OTHER CTA's output travels through
+// distributed shared memory (8 KiB per CTA and step, st.shared::cluster), one cluster barrier per step makes it
+// visible, and each CTA runs the inverse transform of its own output and updates its own accumulator half -- the
+// only state a step of blind rotation needs from the other half is that partial sum.  Against the single-CTA latency
+// kernel: half the transforms per SM (FP64 pipe: 3 + 1 instead of 6 + 2 transforms per step on one SM), 192 threads per
+// CTA so every twiddle is register-resident (no power expansion on the critical path), and the two inverse transforms
+// on different SMs.  Same exactness precondition as the single-CTA latency kernel (a different summation order).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_cplx(uint32_t addr, cplx v) {
+    asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.re), "d"(v.im) : "memory");
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+template <int L>
+__global__ void __launch_bounds__(L * kGroupThreads, 1) blind_rotate_pair_kernel(const BrArgs P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t *acc = reinterpret_cast<uint32_t *>(smem_raw);                                 // this CTA's polynomial, acc_pos order
+    cplx *red = reinterpret_cast<cplx *>(smem_raw + kN * 4);                                 // [L][ab][q][t]: key rows, then products
+    cplx *recv = red + (size_t)L * kBskChunkCplx;                                            // [2 (step parity)][512]: partner's partial sum
+    unsigned char *xbase = reinterpret_cast<unsigned char *>(recv + 2 * kHalfN);
+    constexpr int kXBytes = (kX1Slots + kX2Slots) * 16;
+    uint64_t *key_bar = reinterpret_cast<uint64_t *>(xbase + L * kXBytes);                   // one mbarrier per group
+    uint16_t *atil = reinterpret_cast<uint16_t *>(xbase + L * kXBytes + 64);
+    const int n = P.n, bgbit = P.bgbit;
+    const int tid = threadIdx.x, g = tid >> 6, t = tid & 63, hi = t >> 3, lo = t & 7;
+    const int barid = 1 + g;
+    const uint32_t h = cluster_ctarank();            // which polynomial of the accumulator this CTA owns
+    const size_t ct = blockIdx.x >> 1;
+    const int r = (int)h * L + g;                    // gadget row of this group (trgsw.zig:211-217)
+    cplx *my_red = red + (size_t)g * kBskChunkCplx;
+    const uint64_t policy = l2_policy_evict_last();
+    if (t == 0) {
+        mbar_init(&key_bar[g], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive_expect_tx(&key_bar[g], kBskChunkBytes);
+        bulk_g2s(my_red, P.bsk + (size_t)r * kBskChunkCplx, kBskChunkBytes, &key_bar[g], policy);
+    }
+    Xbuf xb;
+    xb.x1 = reinterpret_cast<cplx *>(xbase + g * kXBytes);
+    xb.x2 = xb.x1 + kX1Slots;
+    xb.flip = 0;
+    Tw2<kTwFull> tw2, tw3;
+#pragma unroll
+    for (int p = 1; p < 8; p++) { tw2.w[p - 1] = P.tw2[tw2_index(p, lo)]; tw3.w[p - 1] = P.tw3[tw3_index(p, t)]; }
+    {   // prologue: gate linear part + modulus switch (both CTAs need every rotation amount)
+        const GateOperands go = gate_operands(P, ct, n);
+        const int op = go.op;
+        for (int i = tid; i <= n; i += L * kGroupThreads) {
+            uint32_t lin = gate_linear_signed(go, i);
+            if (i == n) lin += gate_constant(op);
+            const uint32_t m = (uint32_t)(((unsigned long long)lin + (1u << 20)) >> 21);
+            atil[i] = (uint16_t)((i == n) ? (2 * kN - m) : m);
+        }
+    }
+    __syncthreads();
+    {
+        const int btil = atil[n];
+        const uint32_t *tv = P.testvec ? P.testvec + (P.tv_per_item ? ct * (size_t)(2 * kN) : 0) + h * kN : nullptr;
+        for (int j = tid; j < kN; j += L * kGroupThreads) {
+            const int u = (j - btil) & (2 * kN - 1);
+            const uint32_t v = tv ? tv[u & (kN - 1)] : (h ? 0x20000000u : 0u);   // key.zig:134-145
+            acc[acc_pos(j)] = (u & kN) ? 0u - v : v;
+        }
+    }
+    // the partner's receive buffer, seen from here
+    const uint32_t remote_recv = map_to_cta(smem_u32(recv), h ^ 1u);
+    cluster_arrive();     // both CTAs of the pair are resident and initialised before any remote store
+    cluster_wait();
+
+    const uint32_t mask = (1u << bgbit) - 1u, half_bg = 1u << (bgbit - 1);
+    const int sh = 32 - (g + 1) * bgbit;
+    const int wide = P.wide_round;
+    double margin = 0.0;
+    Producer pr;
+    pr.active = false; pr.remaining = 0;
+    for (int i = 0; i < n; i++) {
+        const int at = atil[i];
+        cplx v[8];
+        {
+            uint32_t d[16];
+            load_rot_diffs(d, acc, at, P.offset, hi, lo);
+            digits_to_cplx(v, d, sh, mask, half_bg);
+        }
+        fwd_transform<false, false, kTwFull, kTwFull>(v, xb, tw2, tw3, hi, lo, barid, pr);
+        mbar_wait(&key_bar[g], (uint32_t)(i & 1));
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            my_red[bsk_slot(0, q, t)] = cmul(v[q], my_red[bsk_slot(0, q, t)]);
+            my_red[bsk_slot(1, q, t)] = cmul(v[q], my_red[bsk_slot(1, q, t)]);
+        }
+        __syncthreads();
+        cplx o[8];
+        // the partial sum of the OTHER output goes to the partner (group L - 1), our own stays in registers (group 0)
+        if (g == L - 1) {
+            const uint32_t other = h ^ 1u;
+#pragma unroll
+            for (int q = 0; q < 8; q++) o[q] = red[other * 512 + q * 64 + t];
+#pragma unroll
+            for (int l = 1; l < L; l++) {
+#pragma unroll
+                for (int q = 0; q < 8; q++) o[q] = cadd(o[q], red[(l * 2 + other) * 512 + q * 64 + t]);
+            }
+            const uint32_t dst = remote_recv + (uint32_t)(((i & 1) * kHalfN + t) * 16);
+#pragma unroll
+            for (int q = 0; q < 8; q++) st_cluster_cplx(dst + q * 64 * 16, o[q]);
+        }
+        if (g == 0) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) o[q] = red[h * 512 + q * 64 + t];
+#pragma unroll
+            for (int l = 1; l < L; l++) {
+#pragma unroll
+                for (int q = 0; q < 8; q++) o[q] = cadd(o[q], red[(l * 2 + h) * 512 + q * 64 + t]);
+            }
+        }
+        cluster_arrive();     // release: our remote stores; also: every local read of `red` is done
+        cluster_wait();       // acquire: the partner's partial sum for our output has landed
+        if (t == 0 && i + 1 < n) {   // prefetch the next step's key row (all products of this step are consumed)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive_expect_tx(&key_bar[g], kBskChunkBytes);
+            bulk_g2s(my_red, P.bsk + ((size_t)(i + 1) * 2 * L + r) * kBskChunkCplx, kBskChunkBytes, &key_bar[g], policy);
+        }
+        if (g == 0) {
+            const cplx *rv = recv + (i & 1) * kHalfN;
+#pragma unroll
+            for (int q = 0; q < 8; q++) o[q] = cadd(o[q], rv[q * 64 + t]);
+            inv_transform<false, false, kTwFull, kTwFull>(o, xb, tw2, tw3, hi, lo, barid, pr);
+            round_accumulate<false>(o, acc, t, wide, margin);
+        }
+        __syncthreads();      // accumulator half complete before the next rotated reads
+    }
+    if (P.out_trlwe) {
+        uint32_t *o = P.out_trlwe + ct * (size_t)(2 * kN) + h * kN;
+        for (int j = tid; j < kN; j += L * kGroupThreads) o[j] = acc[acc_pos(j)];
+    }
+    if (P.out_lv1) {   // sampleExtractIndex(., 0): trlwe.zig:146-162 -- mask from the a half, body from the b half
+        uint32_t *o = P.out_lv1 + ct * (size_t)(kN + 1);
+        if (h == 0) {
+            for (int j = tid; j < kN; j += L * kGroupThreads) o[j] = (j == 0) ? acc[0] : 0u - acc[acc_pos(kN - j)];
+        } else if (tid == 0) {
+            o[kN] = acc[0];
+        }
+    }
+    cluster_arrive();     // neither CTA exits while its shared memory may still be written by the other
+    cluster_wait();
+}
+
+template <int L>
+cudaError_t launch_pair(const BrArgs &a, cudaStream_t s) {
+    const size_t smem = kN * 4 + (size_t)L * kBskChunkBytes + 2 * kHalfN * 16 + (size_t)L * (kX1Slots + kX2Slots) * 16 + 64 + align16((a.n + 1) * 2);
+    auto kern = blind_rotate_pair_kernel<L>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * a.B);
+    cfg.blockDim = dim3(L * kGroupThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, a);
+}
+
 template <int L, bool MARGIN>
 cudaError_t launch_latency(const BrArgs &a, cudaStream_t s) {
     constexpr int G = 2 * L;
@@ -662,6 +843,14 @@ cudaError_t launch_blind_rotate(const BrArgs &a, const BrTuning &tune, bool trac
     const unsigned sm_total = tune.sm_count > 0 ? (unsigned)tune.sm_count : 148u;
     // latency mode: every ciphertext gets an SM of its own; only where the external product is exact
     // (so the different summation order cannot change a rounded coefficient)
+    if (tune.latency_mode == 1 && tune.kct <= 0 && 2 * a.B <= sm_total && !a.wide_round && !track_margin && a.L >= 1 && a.L <= 3) {
+        if (launches) (*launches)++;     // one ciphertext per pair of SMs
+        switch (a.L) {
+            case 1: return launch_pair<1>(a, s);
+            case 2: return launch_pair<2>(a, s);
+            default: return launch_pair<3>(a, s);
+        }
+    }
     if (tune.latency_mode != 0 && tune.kct <= 0 && a.B <= sm_total && !a.wide_round && a.L >= 1 && a.L <= 3) {
         if (launches) (*launches)++;
         switch (a.L) {

@@ -36,7 +36,8 @@ struct BrTuning {
     int kct = 0;        // ciphertexts per CTA (0 = default)
     int use_tma = 1;    // stream key chunks with cp.async.bulk + mbarrier (0: direct global loads)
     int sm_count = 0;   // SMs of the target device (wave-quantisation aware choice of kct)
-    int latency_mode = 1;   // batches <= sm_count: one CTA per ciphertext, transforms of an iteration in parallel
+    int latency_mode = 1;   // batches <= sm_count: one CTA per ciphertext, transforms of an iteration in parallel; batches <=
+                            // sm_count / 2: one two-CTA cluster per ciphertext (2: never the cluster kernel, 0: throughput kernel only)
     int concurrent = 0; // 1: other kernels share the GPU (circuit lanes): pick the CTA width by work per SM-second, not by waves
     int team = 0;       // ciphertexts sharing a warp in adjacent lanes (0 = default, 1, 2)
 };

@@ -191,7 +191,8 @@ cudaError_t launch_keyswitch(const KsArgs &a, int sm_count, cudaStream_t s, uint
     if (a.tile == 4 || a.tile == 8 || a.tile == 16) ct = a.tile;
     const int tiles = (a.B + ct - 1) / ct;
     int splits = 1;
-    while (tiles * splits < 2 * sm_count && splits < 32) splits *= 2;
+    // (up to 256 splits: a single ciphertext then walks 4 mask entries per CTA instead of a 288-step dependent chain)
+    while (tiles * splits < 2 * sm_count && splits < 256) splits *= 2;
     cudaError_t e;
     if (splits > 1) {
         e = cudaMemsetAsync(a.lv0, 0, (size_t)a.B * (a.n + 1) * sizeof(uint32_t), s);
