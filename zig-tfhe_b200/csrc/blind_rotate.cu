@@ -625,8 +625,10 @@ __global__ void __launch_bounds__(2 * L * kGroupThreads, 1) blind_rotate_latency
 // ciphertext.  CTA h owns polynomial h of the accumulator (h = 0: a, 1: b): its L groups of 64 threads transform the L
 // digit polynomials of that half concurrently and multiply them with their key rows (both output parts); the L
 // products per output are summed inside the CTA; the partial sum for the OTHER CTA's output travels through
-// distributed shared memory (8 KiB per CTA and step, st.shared::cluster), one cluster barrier per step makes it
-// visible, and each CTA runs the inverse transform of its own output and updates its own accumulator half -- the
+// distributed shared memory (8 KiB per CTA and step) as asynchronous stores that complete a transaction count on an
+// mbarrier of the receiving CTA (st.async ... mbarrier::complete_tx: no release fence, no cluster barrier inside the
+// loop -- the first version used barrier.cluster per step and spent 15 % of its time in MEMBAR.ALL.GPU / ERRBAR),
+// and each CTA runs the inverse transform of its own output and updates its own accumulator half -- the
 // only state a step of blind rotation needs from the other half is that partial sum.  Against the single-CTA latency
 // kernel: half the transforms per SM (FP64 pipe: 3 + 1 instead of 6 + 2 transforms per step on one SM), 192 threads per
 // CTA so every twiddle is register-resident (no power expansion on the critical path), and the two inverse transforms
@@ -644,6 +646,13 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank
 __device__ __forceinline__ void st_cluster_cplx(uint32_t addr, cplx v) {
     asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.re), "d"(v.im) : "memory");
 }
+// asynchronous remote store that reports its 16 bytes to an mbarrier of the destination CTA: the receiver waits on that
+// barrier's transaction count, no release fence or cluster barrier on either side
+__device__ __forceinline__ void st_async_cplx(uint32_t addr, cplx v, uint32_t remote_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];" ::"r"(addr), "d"(v.re), "d"(v.im),
+                 "r"(remote_mbar)
+                 : "memory");
+}
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
@@ -651,26 +660,30 @@ template <int L>
 __global__ void __launch_bounds__(L * kGroupThreads, 1) blind_rotate_pair_kernel(const BrArgs P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t *acc = reinterpret_cast<uint32_t *>(smem_raw);                                 // this CTA's polynomial, acc_pos order
-    cplx *red = reinterpret_cast<cplx *>(smem_raw + kN * 4);                                 // [L][ab][q][t]: key rows, then products
-    cplx *recv = red + (size_t)L * kBskChunkCplx;                                            // [2 (step parity)][512]: partner's partial sum
+    cplx *red2 = reinterpret_cast<cplx *>(smem_raw + kN * 4);                                // [2 (step parity)][L][ab][q][t]: key rows, then products
+    cplx *recv = red2 + (size_t)2 * L * kBskChunkCplx;                                       // [2 (step parity)][512]: partner's partial sum
     unsigned char *xbase = reinterpret_cast<unsigned char *>(recv + 2 * kHalfN);
     constexpr int kXBytes = (kX1Slots + kX2Slots) * 16;
-    uint64_t *key_bar = reinterpret_cast<uint64_t *>(xbase + L * kXBytes);                   // one mbarrier per group
+    uint64_t *key_bar = reinterpret_cast<uint64_t *>(xbase + L * kXBytes);                   // [2 (step parity)][L] mbarriers
+    uint64_t *recv_bar = key_bar + 2 * L;                                                    // [2 (step parity)]: partner's partial sum landed
     uint16_t *atil = reinterpret_cast<uint16_t *>(xbase + L * kXBytes + 64);
+    // Key rows are double-buffered: the row of step i + 1 is requested at the top of step i (its buffer held the products
+    // of step i - 1, all consumed before that step's cluster barrier), so the bulk copy has a whole step to land.
     const int n = P.n, bgbit = P.bgbit;
     const int tid = threadIdx.x, g = tid >> 6, t = tid & 63, hi = t >> 3, lo = t & 7;
     const int barid = 1 + g;
     const uint32_t h = cluster_ctarank();            // which polynomial of the accumulator this CTA owns
     const size_t ct = blockIdx.x >> 1;
     const int r = (int)h * L + g;                    // gadget row of this group (trgsw.zig:211-217)
-    cplx *my_red = red + (size_t)g * kBskChunkCplx;
     const uint64_t policy = l2_policy_evict_last();
     if (t == 0) {
         mbar_init(&key_bar[g], 1);
+        mbar_init(&key_bar[L + g], 1);
+        if (g == 0) { mbar_init(&recv_bar[0], 1); mbar_init(&recv_bar[1], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive_expect_tx(&key_bar[g], kBskChunkBytes);
-        bulk_g2s(my_red, P.bsk + (size_t)r * kBskChunkCplx, kBskChunkBytes, &key_bar[g], policy);
+        bulk_g2s(red2 + (size_t)g * kBskChunkCplx, P.bsk + (size_t)r * kBskChunkCplx, kBskChunkBytes, &key_bar[g], policy);
     }
     Xbuf xb;
     xb.x1 = reinterpret_cast<cplx *>(xbase + g * kXBytes);
@@ -701,6 +714,7 @@ __global__ void __launch_bounds__(L * kGroupThreads, 1) blind_rotate_pair_kernel
     }
     // the partner's receive buffer, seen from here
     const uint32_t remote_recv = map_to_cta(smem_u32(recv), h ^ 1u);
+    const uint32_t remote_bar = map_to_cta(smem_u32(recv_bar), h ^ 1u);
     cluster_arrive();     // both CTAs of the pair are resident and initialised before any remote store
     cluster_wait();
 
@@ -712,6 +726,15 @@ __global__ void __launch_bounds__(L * kGroupThreads, 1) blind_rotate_pair_kernel
     pr.active = false; pr.remaining = 0;
     for (int i = 0; i < n; i++) {
         const int at = atil[i];
+        cplx *red = red2 + (size_t)(i & 1) * L * kBskChunkCplx;
+        cplx *my_red = red + (size_t)g * kBskChunkCplx;
+        if (t == 0 && i + 1 < n) {   // request the next step's key row into the other buffer
+            const int nb = (i + 1) & 1;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive_expect_tx(&key_bar[nb * L + g], kBskChunkBytes);
+            bulk_g2s(red2 + ((size_t)nb * L + g) * kBskChunkCplx, P.bsk + ((size_t)(i + 1) * 2 * L + r) * kBskChunkCplx, kBskChunkBytes,
+                     &key_bar[nb * L + g], policy);
+        }
         cplx v[8];
         {
             uint32_t d[16];
@@ -719,12 +742,13 @@ __global__ void __launch_bounds__(L * kGroupThreads, 1) blind_rotate_pair_kernel
             digits_to_cplx(v, d, sh, mask, half_bg);
         }
         fwd_transform<false, false, kTwFull, kTwFull>(v, xb, tw2, tw3, hi, lo, barid, pr);
-        mbar_wait(&key_bar[g], (uint32_t)(i & 1));
+        mbar_wait(&key_bar[(i & 1) * L + g], (uint32_t)((i >> 1) & 1));
 #pragma unroll
         for (int q = 0; q < 8; q++) {
             my_red[bsk_slot(0, q, t)] = cmul(v[q], my_red[bsk_slot(0, q, t)]);
             my_red[bsk_slot(1, q, t)] = cmul(v[q], my_red[bsk_slot(1, q, t)]);
         }
+        if (tid == 0) mbar_arrive_expect_tx(&recv_bar[i & 1], kHalfN * 16);   // this step's 8 KiB from the partner
         __syncthreads();
         cplx o[8];
         // the partial sum of the OTHER output goes to the partner (group L - 1), our own stays in registers (group 0)
@@ -739,7 +763,7 @@ __global__ void __launch_bounds__(L * kGroupThreads, 1) blind_rotate_pair_kernel
             }
             const uint32_t dst = remote_recv + (uint32_t)(((i & 1) * kHalfN + t) * 16);
 #pragma unroll
-            for (int q = 0; q < 8; q++) st_cluster_cplx(dst + q * 64 * 16, o[q]);
+            for (int q = 0; q < 8; q++) st_async_cplx(dst + q * 64 * 16, o[q], remote_bar + (uint32_t)((i & 1) * 8));
         }
         if (g == 0) {
 #pragma unroll
@@ -750,14 +774,8 @@ __global__ void __launch_bounds__(L * kGroupThreads, 1) blind_rotate_pair_kernel
                 for (int q = 0; q < 8; q++) o[q] = cadd(o[q], red[(l * 2 + h) * 512 + q * 64 + t]);
             }
         }
-        cluster_arrive();     // release: our remote stores; also: every local read of `red` is done
-        cluster_wait();       // acquire: the partner's partial sum for our output has landed
-        if (t == 0 && i + 1 < n) {   // prefetch the next step's key row (all products of this step are consumed)
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive_expect_tx(&key_bar[g], kBskChunkBytes);
-            bulk_g2s(my_red, P.bsk + ((size_t)(i + 1) * 2 * L + r) * kBskChunkCplx, kBskChunkBytes, &key_bar[g], policy);
-        }
         if (g == 0) {
+            mbar_wait(&recv_bar[i & 1], (uint32_t)((i >> 1) & 1));   // the partner's 512 asynchronous stores have completed
             const cplx *rv = recv + (i & 1) * kHalfN;
 #pragma unroll
             for (int q = 0; q < 8; q++) o[q] = cadd(o[q], rv[q * 64 + t]);
@@ -784,7 +802,7 @@ __global__ void __launch_bounds__(L * kGroupThreads, 1) blind_rotate_pair_kernel
 
 template <int L>
 cudaError_t launch_pair(const BrArgs &a, cudaStream_t s) {
-    const size_t smem = kN * 4 + (size_t)L * kBskChunkBytes + 2 * kHalfN * 16 + (size_t)L * (kX1Slots + kX2Slots) * 16 + 64 + align16((a.n + 1) * 2);
+    const size_t smem = kN * 4 + (size_t)2 * L * kBskChunkBytes + 2 * kHalfN * 16 + (size_t)L * (kX1Slots + kX2Slots) * 16 + 64 + align16((a.n + 1) * 2);
     auto kern = blind_rotate_pair_kernel<L>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
