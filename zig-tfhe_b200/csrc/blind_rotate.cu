@@ -27,6 +27,8 @@
 // No tensor cores: the pointwise MAC is not a contraction and the 512-point transforms are FP64.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include "br_common.cuh"
 #include "kernels.cuh"
 #include "negacyclic_fft.cuh"
@@ -298,7 +300,7 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
     xb.x2 = reinterpret_cast<cplx *>(gb + Lay::kAccBytes + Lay::kX1Bytes);
     xb.flip = 0;
     uint16_t *atil = reinterpret_cast<uint16_t *>(gb + Lay::kAccBytes + Lay::kX1Bytes + (DBX2 ? 2 : 1) * Lay::kX2Bytes);
-    const size_t ct = (size_t)first_ct + (live ? g : g - 1);
+    const size_t ct = (size_t)P.ct_base + first_ct + (live ? g : g - 1);
 
     // per-thread twiddles: role B node q2 = lo, role C node t
     Tw2<POW> tw2;
@@ -502,7 +504,7 @@ __global__ void __launch_bounds__(2 * L * kGroupThreads, 1) blind_rotate_latency
     const int n = P.n, bgbit = P.bgbit;
     const int tid = threadIdx.x, g = tid >> 6, t = tid & 63, hi = t >> 3, lo = t & 7;
     const int barid = 1 + g;
-    const size_t ct = blockIdx.x;
+    const size_t ct = (size_t)P.ct_base + blockIdx.x;
     // Key row r of iteration i lands by cp.async.bulk directly in this group's slice of the reduction buffer
     // (identical [ab][q][t] layout): the thread that reads a key value overwrites it with its product.
     cplx *my_red = red + (size_t)g * kBskChunkCplx;
@@ -673,7 +675,7 @@ __global__ void __launch_bounds__(L * kGroupThreads, 1) blind_rotate_pair_kernel
     const int tid = threadIdx.x, g = tid >> 6, t = tid & 63, hi = t >> 3, lo = t & 7;
     const int barid = 1 + g;
     const uint32_t h = cluster_ctarank();            // which polynomial of the accumulator this CTA owns
-    const size_t ct = blockIdx.x >> 1;
+    const size_t ct = (size_t)P.ct_base + (blockIdx.x >> 1);
     const int r = (int)h * L + g;                    // gadget row of this group (trgsw.zig:211-217)
     const uint64_t policy = l2_policy_evict_last();
     if (t == 0) {
@@ -879,6 +881,30 @@ cudaError_t launch_blind_rotate(const BrArgs &a, const BrTuning &tune, bool trac
     }
     int kct = tune.kct;
     if (kct <= 0 && tune.concurrent != 0) kct = 4;   // densest CTA (ciphertexts per SM-second); idle SMs go to the other lanes
+    if (kct <= 0 && tune.use_tma != 0 && a.ct_base == 0) {
+        // Mid-size batches: whole waves of the densest CTA (KCT = 4), then the remainder as its own launch with whatever
+        // width is cheapest for it -- e.g. 2,048 ciphertexts = 3 waves x 6.5 ms + 272 ciphertexts at KCT = 2 (4.5 ms)
+        // instead of 4 waves (26 ms).  Ciphertext indices stay global (BrArgs.ct_base), so no pointer is offset.
+        const unsigned wave = sm_total * 4;
+        const unsigned full = (a.B / wave) * wave, tail = a.B - full;
+        if (full > 0 && tail > 0) {
+            static const double t_cta[5] = {0.0, 4.5, 4.5, 6.1, 6.5};
+            double best_tail = 1e30;
+            for (int k = 1; k <= 4; k++) best_tail = std::min(best_tail, ((tail + sm_total * k - 1) / (sm_total * k)) * t_cta[k]);
+            if (tune.latency_mode != 0 && tail <= sm_total && !a.wide_round) best_tail = std::min(best_tail, 2.5);
+            if (best_tail < t_cta[4] - 1e-9) {
+                BrArgs m = a, r = a;
+                m.B = full;
+                r.B = tail;
+                r.ct_base = full;
+                BrTuning tm = tune;
+                tm.kct = 4;
+                cudaError_t e = launch_blind_rotate(m, tm, track_margin, s, launches);
+                if (e != cudaSuccess) return e;
+                return launch_blind_rotate(r, tune, track_margin, s, launches);
+            }
+        }
+    }
     if (kct <= 0) {
         // minimise (number of CTA waves) x (time of one CTA at that width); CTA times measured on B200 at n = 700
         // (profiles/r01_first_light*.log, profiles/r01_wave_scaling.log): 1 or 2 ciphertexts 4.5 ms, 3: 6.1 ms, 4: 6.5 ms.

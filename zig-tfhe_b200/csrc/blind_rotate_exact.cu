@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(kThreads, 2) blind_rotate_exact_kernel(const B
     uint16_t *atil = reinterpret_cast<uint16_t *>(diff + kN);
     const int n = P.n, L = P.L, bgbit = P.bgbit;
     const int j = threadIdx.x;
-    const size_t ct = blockIdx.x;
+    const size_t ct = (size_t)P.ct_base + blockIdx.x;
 
     for (int i = j; i < 6 * kTabStride; i += kThreads) tab[i] = tables[i];
     const double *twist_re = tab, *twist_im = tab + kTabStride;

@@ -26,7 +26,8 @@ struct BrArgs {
     uint32_t *out_lv1;      // [B][N+1] sampleExtractIndex(.,0), or nullptr
     uint32_t *out_trlwe;    // [B][2][N] accumulator, or nullptr
     unsigned long long *margin_bits;  // global max |t-round(t)| as double bits (MARGIN variant), or nullptr
-    uint32_t B;
+    uint32_t B;             // ciphertexts of THIS launch
+    uint32_t ct_base;       // index of its first ciphertext in the arrays above (a batch split into several launches)
     int n, L, bgbit;
     uint32_t offset;        // CloudKey.decomposition_offset
     int wide_round;         // 1: F2I.S64 rounding (large-digit sets), 0: magic-add rounding
