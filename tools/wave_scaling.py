@@ -23,10 +23,10 @@ ctx.set_tuning("timing", 1)
 for kv in sys.argv[1:]:
     k, v = kv.split("=")
     ctx.set_tuning(k, int(v))
-for kct in (6, 4):
+for kct in [int(k) for k in os.environ.get("KCTS", "6,4").split(",")]:
     ctx.set_tuning("kct", kct)
     for waves in [int(w) for w in os.environ.get("WAVES", "1,2,4,8,16,37,74").split(",")]:
-        B = 148 * kct * waves
+        B = 592 * waves if os.environ.get("FIXED_WAVE") else 148 * kct * waves
         ctx.gate_batch(tfhe_b200.NAND, CA[:B], CB[:B])
         ms = ctx.last_kernel_ms(0, 0)
         print(f"kct={kct} waves={waves:3d} B={B:6d} K1={ms:8.2f} ms  {ms / waves:6.2f} ms/wave  {B / ms * 1e3:9.0f} bootstraps/s", flush=True)

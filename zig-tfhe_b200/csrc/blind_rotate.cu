@@ -210,7 +210,8 @@ struct Layout {
     static constexpr int kTw2Mode = kTwShared ? kTwSmem : (KCT > 4 ? kTwPow : kTwFull);   // KCT = 5, 6 without teams: keep r, r^2, r^4
     static constexpr int kTw3Mode = kTwShared ? kTwSmem : (KCT > 5 ? kTwPow : kTwFull);
     static constexpr bool kDbX2 = KCT <= 4;     // double-buffered X2 (fits when only 4 groups share the SM)
-    static constexpr int kStages = 3;   // key-ring depth (4 measured no faster)
+    static constexpr int kStages = 3;   // key-ring depth (4 measured no faster; KCT = 2 with a 2-deep ring and two CTAs, i.e. two
+                                        // independent rings, per SM: 91.0 k/s, same as one KCT = 4 CTA -- ring coupling is not a limiter)
     static constexpr bool kAccTmem = !kTwShared && KCT > 5;   // MAC accumulators in TMEM (measured slower than KCT = 4)
     static constexpr int kTmemCols = 256;       // 64 columns per warp, up to 3 warps per TMEM quadrant
     static constexpr int kAccBytes = 2 * kN * 4;
