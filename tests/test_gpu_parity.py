@@ -235,3 +235,31 @@ def test_latency_mode_equals_throughput_mode(ctx128, orc128, keys128):
         assert 0.0 < ctx128.max_round_margin(reset=True) < 0.25
     finally:
         ctx128.track_margin(False)
+
+
+def test_split_launch_full_waves_plus_tail(ctx128, orc128, keys128):
+    """a batch that is not a whole number of CTA waves runs as (full waves at KCT = 4) + (tail launch with its own
+    kernel: here 5 ciphertexts on the cluster latency kernel) over global ciphertext indices; per-item opcodes and
+    per-item test vectors follow the indices"""
+    B = 148 * 4 + 5
+    a, b, ca, cb = _enc_pairs(orc128, keys128, B, seed=21)
+    ops = (np.arange(B) % 10).astype(np.int32)
+    split = ctx128.gate_batch(ops, ca, cb)
+    ctx128.set_tuning("kct", 4)                      # explicit width: one launch
+    try:
+        one = ctx128.gate_batch(ops, ca, cb)
+    finally:
+        ctx128.set_tuning("kct", 0)
+    assert (split == one).all()
+    from conftest import TRUTH
+    want = np.array([TRUTH[int(ops[i])](int(a[i]), int(b[i])) for i in range(B)], np.uint8)
+    assert (orc128.decrypt_bools(split, keys128) == want).all()
+    tail = slice(B - 7, B)
+    ref = np.stack([orc128.gate(int(ops[i]), ca[i], cb[i], keys128) for i in range(B - 7, B)])
+    assert (split[tail] == ref).all()
+    # per-item test vectors across the split (programmable bootstrap, trgsw.zig:336-400)
+    rng = np.random.default_rng(5)
+    tv = rng.integers(0, 2**32, (B, 2, 1024), dtype=np.uint32)
+    got = ctx128.blind_rotate_batch(ca, tv, tv_per_item=True)
+    for i in (0, 591, 592, B - 1):
+        assert (got[i] == orc128.blind_rotate_batch(ca[i:i + 1], keys128, tv[i])[0]).all(), i
