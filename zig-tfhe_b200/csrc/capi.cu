@@ -753,70 +753,83 @@ int tfhe_b200_circuit_info(const tfhe_b200_circuit *q, size_t *n_levels, size_t 
     return 0;
 }
 
-int tfhe_b200_circuit_run(tfhe_b200_ctx *c, tfhe_b200_circuit *q, const uint32_t *inputs, uint32_t *outputs, size_t instances) {
-    if (!c || !q || q->ctx != c) return fail(c, TFHE_B200_ERR_INVALID, "circuit belongs to another context");
-    if (!c->has_key || !c->has_ksk) return fail(c, TFHE_B200_ERR_NO_KEY, "no cloud key loaded");
-    if (instances == 0) return 0;
-    if ((q->n_inputs && !inputs) || (!q->outputs.empty() && !outputs)) return fail(c, TFHE_B200_ERR_INVALID, "null buffer");
+// all lanes of ONE device: passes of (inputs + every level in flight on every lane) -> (results back) -> (lanes drained)
+static int circuit_run_device(tfhe_b200_ctx *c, tfhe_b200_circuit *q, int k, const uint32_t *inputs, uint32_t *outputs, size_t instances,
+                              size_t dlo, size_t dhi, size_t per_pass) {
     const size_t w0 = (size_t)c->prm.n + 1, w1 = (size_t)kN + 1;
-    const int nd = (int)c->devs.size(), nv = nd * q->lanes;
-    // instances per pass: bounded by the launch chunk and by ~8 GiB of wire storage per device
-    size_t per_pass = std::max<size_t>(1, c->max_chunk / std::max<size_t>(q->max_width, 1));
-    per_pass = std::min(per_pass, std::max<size_t>(1, ((size_t)8 << 30) / (q->n_slots * w0 * 4 * q->lanes)));
-    // contiguous instance ranges: first over devices, then over the lanes of a device
-    std::vector<size_t> hi(nv), pos(nv), cur(nv);
-    for (int k = 0; k < nd; k++) {
-        const size_t dlo = instances * k / nd, dhi = instances * (k + 1) / nd;
-        for (int l = 0; l < q->lanes; l++) {
-            pos[k * q->lanes + l] = dlo + (dhi - dlo) * l / q->lanes;
-            hi[k * q->lanes + l] = dlo + (dhi - dlo) * (l + 1) / q->lanes;
-        }
+    const int nl = q->lanes;
+    Device &d = c->devs[k];
+    std::vector<size_t> hi(nl), pos(nl), cur(nl);
+    for (int l = 0; l < nl; l++) {
+        pos[l] = dlo + (dhi - dlo) * l / nl;
+        hi[l] = dlo + (dhi - dlo) * (l + 1) / nl;
     }
+    CU(c, cudaSetDevice(d.id));
     bool more = true;
     while (more) {
         more = false;
-        for (int v = 0; v < nv; v++) {          // phase 1: inputs + all levels in flight on every lane of every device
-            Device &d = c->devs[v / q->lanes];
-            auto &pd = q->dev[v];
-            const size_t inst = std::min(per_pass, hi[v] - pos[v]);
-            cur[v] = inst;
+        for (int l = 0; l < nl; l++) {
+            auto &pd = q->dev[k * nl + l];
+            const size_t inst = std::min(per_pass, hi[l] - pos[l]);
+            cur[l] = inst;
             if (inst == 0) continue;
-            CU(c, cudaSetDevice(d.id));
             const void *old_w = pd.wires.p, *old_l = pd.lv1.p;
             if (int r = ensure(c, pd.wires, q->n_slots * inst * w0 * 4)) return r;
             if (int r = ensure(c, pd.lv1, std::max<size_t>(q->max_width, 1) * inst * w1 * 4)) return r;
             if ((old_w != pd.wires.p || old_l != pd.lv1.p) && pd.graph) { cudaGraphExecDestroy(pd.graph); pd.graph = nullptr; }
             uint32_t *wires = (uint32_t *)pd.wires.p;
             for (size_t i = 0; i < q->n_inputs; i++)
-                CU(c, cudaMemcpyAsync(wires + i * inst * w0, inputs + (i * instances + pos[v]) * w0, inst * w0 * 4, cudaMemcpyHostToDevice, pd.stream));
+                CU(c, cudaMemcpyAsync(wires + i * inst * w0, inputs + (i * instances + pos[l]) * w0, inst * w0 * 4, cudaMemcpyHostToDevice, pd.stream));
             if (int r = circuit_enqueue(c, q, d, pd, inst)) return r;
         }
-        for (int v = 0; v < nv; v++) {          // phase 2: results back (pageable D2H blocks the host per lane)
-            Device &d = c->devs[v / q->lanes];
-            auto &pd = q->dev[v];
-            const size_t inst = cur[v];
+        for (int l = 0; l < nl; l++) {          // results back (a pageable D2H blocks this thread until the lane is done)
+            auto &pd = q->dev[k * nl + l];
+            const size_t inst = cur[l];
             if (inst == 0) continue;
-            CU(c, cudaSetDevice(d.id));
             const uint32_t *wires = (const uint32_t *)pd.wires.p;
             for (size_t o = 0; o < q->outputs.size(); o++) {
                 const uint32_t ref = q->outputs[o];
                 const uint32_t *src = wires + (size_t)(ref & ~TFHE_B200_WIRE_NOT) * inst * w0;
                 if (ref & TFHE_B200_WIRE_NOT) {   // Gates.notGate of the wire (src/gates.zig:131-133)
                     if (int r = ensure(c, pd.neg, inst * w0 * 4)) return r;
-                    CU(c, launch_negate(src, (uint32_t *)pd.neg.p, inst * w0, pd.stream, &c->launches));
+                    CU(c, launch_negate(src, (uint32_t *)pd.neg.p, inst * w0, pd.stream, &d.launches));
                     src = (const uint32_t *)pd.neg.p;
                 }
-                CU(c, cudaMemcpyAsync(outputs + (o * instances + pos[v]) * w0, src, inst * w0 * 4, cudaMemcpyDeviceToHost, pd.stream));
+                CU(c, cudaMemcpyAsync(outputs + (o * instances + pos[l]) * w0, src, inst * w0 * 4, cudaMemcpyDeviceToHost, pd.stream));
                 if (ref & TFHE_B200_WIRE_NOT) CU(c, cudaStreamSynchronize(pd.stream));   // pd.neg is reused by the next output
             }
         }
-        for (int v = 0; v < nv; v++) {
-            CU(c, cudaSetDevice(c->devs[v / q->lanes].id));
-            CU(c, cudaStreamSynchronize(q->dev[v].stream));
-            pos[v] += cur[v];
-            if (pos[v] < hi[v]) more = true;
+        for (int l = 0; l < nl; l++) {
+            CU(c, cudaStreamSynchronize(q->dev[k * nl + l].stream));
+            pos[l] += cur[l];
+            if (pos[l] < hi[l]) more = true;
         }
     }
+    return 0;
+}
+
+int tfhe_b200_circuit_run(tfhe_b200_ctx *c, tfhe_b200_circuit *q, const uint32_t *inputs, uint32_t *outputs, size_t instances) {
+    if (!c || !q || q->ctx != c) return fail(c, TFHE_B200_ERR_INVALID, "circuit belongs to another context");
+    if (!c->has_key || !c->has_ksk) return fail(c, TFHE_B200_ERR_NO_KEY, "no cloud key loaded");
+    if (instances == 0) return 0;
+    if ((q->n_inputs && !inputs) || (!q->outputs.empty() && !outputs)) return fail(c, TFHE_B200_ERR_INVALID, "null buffer");
+    const size_t w0 = (size_t)c->prm.n + 1;
+    const int nd = (int)c->devs.size();
+    // instances per pass: bounded by the launch chunk and by ~8 GiB of wire storage per device
+    size_t per_pass = std::max<size_t>(1, c->max_chunk / std::max<size_t>(q->max_width, 1));
+    per_pass = std::min(per_pass, std::max<size_t>(1, ((size_t)8 << 30) / (q->n_slots * w0 * 4 * q->lanes)));
+    // contiguous instance ranges per device (then per lane); one host thread per device, as in run_host
+    if (nd == 1) return circuit_run_device(c, q, 0, inputs, outputs, instances, 0, instances, per_pass);
+    std::vector<int> rc(nd, 0);
+    std::vector<std::thread> workers;
+    for (int k = 0; k < nd; k++) {
+        const size_t dlo = instances * k / nd, dhi = instances * (k + 1) / nd;
+        if (dlo == dhi) continue;
+        workers.emplace_back([=, &rc] { rc[k] = circuit_run_device(c, q, k, inputs, outputs, instances, dlo, dhi, per_pass); });
+    }
+    for (auto &w : workers) w.join();
+    for (int k = 0; k < nd; k++)
+        if (rc[k]) return rc[k];
     return 0;
 }
 
