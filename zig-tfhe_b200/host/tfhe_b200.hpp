@@ -47,6 +47,15 @@ public:
         if (rc) throw Error(rc, "no sm_100 CUDA device / bad parameters");
         check(tfhe_b200_load_key(ctx_, ck.bootstrapping_key, ck.key_switching_key, (size_t)words_ * 4, ck.decomposition_offset));
     }
+    // key.CloudKey.new on the device (key.zig:70-77, 148-212): the evaluation keys are generated where they are used, from the
+    // secret key the caller holds; nothing but the 6.9 KB secret key crosses the bus
+    GpuBootstrap(const tfhe_b200_params &p, const uint32_t *key_lv0, const uint32_t *key_lv1, uint64_t seed, double ksk_alpha,
+                 double bsk_alpha, const std::vector<int> &devices = {0})
+        : words_(p.n + 1) {
+        int rc = tfhe_b200_create(&p, devices.data(), (int)devices.size(), &ctx_);
+        if (rc) throw Error(rc, "no sm_100 CUDA device / bad parameters");
+        check(tfhe_b200_keygen(ctx_, key_lv0, key_lv1, seed, ksk_alpha, bsk_alpha, nullptr, nullptr));
+    }
     GpuBootstrap(const GpuBootstrap &) = delete;
     GpuBootstrap &operator=(const GpuBootstrap &) = delete;
     ~GpuBootstrap() { tfhe_b200_destroy(ctx_); }
@@ -61,6 +70,13 @@ public:
     Ciphertext bootstrapWithoutKeySwitch(const Ciphertext &c) const {
         Ciphertext out(words_);
         check(tfhe_b200_bootstrap_no_keyswitch_batch(ctx_, c.data(), out.data(), 1));
+        return out;
+    }
+    // the bootstrapLut src/lut.zig:42 documents: `table[x]` = torus value to return for message x (Encoder.encode(f(x)),
+    // lut/encoder.zig:66-73); the LookupTable (lut/generator.zig:150-191) is built on the device
+    Ciphertext bootstrapLut(const Ciphertext &c, const std::vector<uint32_t> &table) const {
+        Ciphertext out(words_);
+        check(tfhe_b200_lut_bootstrap_batch(ctx_, c.data(), out.data(), 1, table.data(), (int)table.size(), 0));
         return out;
     }
     const char *name() const { return "b200"; }
