@@ -174,6 +174,10 @@ typedef struct tfhe_b200_circuit tfhe_b200_circuit;
 int tfhe_b200_circuit_create(tfhe_b200_ctx *ctx, const tfhe_b200_gate_node *gates, size_t n_gates, size_t n_inputs,
                              const uint32_t *outputs, size_t n_outputs, tfhe_b200_circuit **out);
 void tfhe_b200_circuit_destroy(tfhe_b200_circuit *circuit);
+/* The host-only half of circuit_create (no device, no context): validates the netlist and reports the number of dependency
+ * levels, the widest level and (gate_level != NULL) the level of every gate, 1-based.  Same error codes as circuit_create. */
+int tfhe_b200_circuit_plan(const tfhe_b200_gate_node *gates, size_t n_gates, size_t n_inputs, const uint32_t *outputs,
+                           size_t n_outputs, size_t *n_levels, size_t *max_level_width, uint32_t *gate_level);
 int tfhe_b200_circuit_info(const tfhe_b200_circuit *circuit, size_t *n_levels, size_t *max_level_width, size_t *n_gates);
 /* inputs: [n_inputs][instances][n+1], outputs: [n_outputs][instances][n+1] (host buffers, wire-major). */
 int tfhe_b200_circuit_run(tfhe_b200_ctx *ctx, tfhe_b200_circuit *circuit, const uint32_t *inputs, uint32_t *outputs,

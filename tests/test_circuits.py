@@ -156,6 +156,23 @@ def test_adder_netlist_is_the_reference_full_adder_chain():
     assert (total == x + y + cin).all() and total[0] == 706
 
 
+def test_circuit_plan_levels_without_a_gpu():
+    """tfhe_b200_circuit_plan is the host-only half of circuit_create: the 16-bit adder has 1 + 2 * 16 levels, the first one
+    32 gates wide; invalid netlists are rejected with the same codes"""
+    import tfhe_b200
+    from tfhe_b200 import circuits
+    gates, n_in, outs = circuits.ripple_carry_netlist(16)
+    levels, width, gl = tfhe_b200.circuit_plan(gates, n_in, outs)
+    assert (levels, width) == (33, 32)
+    assert (gl[0::5] == 1).all() and (gl[1::5] == 1).all()                     # every a^b and a&b: level 1
+    assert list(gl[2::5]) == [2 * i + 2 for i in range(16)] == list(gl[3::5])  # (a^b)&c and the sum bit of bit i
+    assert list(gl[4::5]) == [2 * i + 3 for i in range(16)]                    # carry out of bit i
+    assert tfhe_b200.circuit_plan([], 3, [0, 2 | tfhe_b200.WIRE_NOT])[:2] == (0, 0)   # wires only
+    for bad_gates, bad_outs in (([(0, 0, 3)], [2]), ([(17, 0, 1)], [2]), ([(0, 0, 1)], [9])):
+        with pytest.raises(tfhe_b200.TfheB200Error):
+            tfhe_b200.circuit_plan(bad_gates, 2, bad_outs)
+
+
 @pytest.mark.gpu
 def test_native_circuit_equals_level_batched_python_and_oracle():
     import tfhe_b200

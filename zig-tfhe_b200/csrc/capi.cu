@@ -658,24 +658,68 @@ int tfhe_b200_keyswitch_batch_device(tfhe_b200_ctx *c, int dev, const uint32_t *
 }
 
 
-int tfhe_b200_circuit_create(tfhe_b200_ctx *c, const tfhe_b200_gate_node *gates, size_t n_gates, size_t n_inputs,
-                             const uint32_t *outputs, size_t n_outputs, tfhe_b200_circuit **out) {
-    if (!c || !out || (!gates && n_gates) || (!outputs && n_outputs)) return fail(c, TFHE_B200_ERR_INVALID, "null argument");
-    *out = nullptr;
+// host-only part of circuit compilation (no device needed): validation + dependency level of every gate
+static int circuit_plan(const tfhe_b200_gate_node *gates, size_t n_gates, size_t n_inputs, const uint32_t *outputs, size_t n_outputs,
+                        std::vector<uint32_t> &level, uint32_t &depth, std::string &why) {
+    char buf[160];
     const size_t n_wires = n_inputs + n_gates;
-    if (n_wires == 0 || n_wires >= 0x7fffffffu) return fail(c, TFHE_B200_ERR_INVALID, "bad circuit size");
+    if ((!gates && n_gates) || (!outputs && n_outputs)) { why = "null argument"; return TFHE_B200_ERR_INVALID; }
+    if (n_wires == 0 || n_wires >= 0x7fffffffu) { why = "bad circuit size"; return TFHE_B200_ERR_INVALID; }
     const uint32_t kNot = TFHE_B200_WIRE_NOT;
-    std::vector<uint32_t> level(n_wires, 0);
-    uint32_t depth = 0;
+    level.assign(n_wires, 0);
+    depth = 0;
     for (size_t g = 0; g < n_gates; g++) {
         const uint32_t a = gates[g].a & ~kNot, b = gates[g].b & ~kNot;
-        if (gates[g].op < 0 || gates[g].op > 9) return fail(c, TFHE_B200_ERR_INVALID, "gate %zu: bad opcode %d", g, gates[g].op);
-        if (a >= n_inputs + g || b >= n_inputs + g) return fail(c, TFHE_B200_ERR_INVALID, "gate %zu reads a wire defined later (not topological)", g);
+        if (gates[g].op < 0 || gates[g].op > 9) {
+            snprintf(buf, sizeof(buf), "gate %zu: bad opcode %d", g, gates[g].op);
+            why = buf;
+            return TFHE_B200_ERR_INVALID;
+        }
+        if (a >= n_inputs + g || b >= n_inputs + g) {
+            snprintf(buf, sizeof(buf), "gate %zu reads a wire defined later (not topological)", g);
+            why = buf;
+            return TFHE_B200_ERR_INVALID;
+        }
         level[n_inputs + g] = 1 + std::max(level[a], level[b]);
         depth = std::max(depth, level[n_inputs + g]);
     }
     for (size_t o = 0; o < n_outputs; o++)
-        if ((outputs[o] & ~kNot) >= n_wires) return fail(c, TFHE_B200_ERR_INVALID, "output %zu: no such wire", o);
+        if ((outputs[o] & ~kNot) >= n_wires) {
+            snprintf(buf, sizeof(buf), "output %zu: no such wire", o);
+            why = buf;
+            return TFHE_B200_ERR_INVALID;
+        }
+    return 0;
+}
+
+int tfhe_b200_circuit_plan(const tfhe_b200_gate_node *gates, size_t n_gates, size_t n_inputs, const uint32_t *outputs, size_t n_outputs,
+                           size_t *n_levels, size_t *max_level_width, uint32_t *gate_level) {
+    std::vector<uint32_t> level;
+    uint32_t depth = 0;
+    std::string why;
+    if (int r = circuit_plan(gates, n_gates, n_inputs, outputs, n_outputs, level, depth, why)) return r;
+    std::vector<size_t> width(depth + 1, 0);
+    for (size_t g = 0; g < n_gates; g++) {
+        width[level[n_inputs + g]]++;
+        if (gate_level) gate_level[g] = level[n_inputs + g];
+    }
+    if (n_levels) *n_levels = depth;
+    if (max_level_width) *max_level_width = depth ? *std::max_element(width.begin() + 1, width.end()) : 0;
+    return 0;
+}
+
+int tfhe_b200_circuit_create(tfhe_b200_ctx *c, const tfhe_b200_gate_node *gates, size_t n_gates, size_t n_inputs,
+                             const uint32_t *outputs, size_t n_outputs, tfhe_b200_circuit **out) {
+    if (!c || !out) return fail(c, TFHE_B200_ERR_INVALID, "null argument");
+    *out = nullptr;
+    const size_t n_wires = n_inputs + n_gates;
+    const uint32_t kNot = TFHE_B200_WIRE_NOT;
+    std::vector<uint32_t> level;
+    uint32_t depth = 0;
+    {
+        std::string why;
+        if (int r = circuit_plan(gates, n_gates, n_inputs, outputs, n_outputs, level, depth, why)) return fail(c, r, "%s", why.c_str());
+    }
     auto *q = new tfhe_b200_circuit();
     q->ctx = c;
     q->n_inputs = n_inputs; q->n_gates = n_gates; q->n_slots = n_wires;

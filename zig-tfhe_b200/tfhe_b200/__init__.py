@@ -125,6 +125,7 @@ def load_library():
         "tfhe_b200_lut_generate": (i32, [vp, vp, i32, vp]),
         "tfhe_b200_circuit_create": (i32, [vp, vp, sz, sz, vp, sz, vp]),
         "tfhe_b200_circuit_destroy": (None, [vp]),
+        "tfhe_b200_circuit_plan": (i32, [vp, sz, sz, vp, sz, vp, vp, vp]),
         "tfhe_b200_circuit_info": (i32, [vp, vp, vp, vp]),
         "tfhe_b200_circuit_run": (i32, [vp, vp, vp, vp, sz]),
     }
@@ -146,7 +147,7 @@ EXPORTED_SYMBOLS = [
     "tfhe_b200_set_tuning", "tfhe_b200_measure_fp64_tflops", "tfhe_b200_last_kernel_ms",
     "tfhe_b200_load_reencryption_key", "tfhe_b200_reencrypt_batch",
     "tfhe_b200_keygen", "tfhe_b200_decomposition_offset", "tfhe_b200_lut_bootstrap_batch", "tfhe_b200_lut_generate",
-    "tfhe_b200_circuit_create", "tfhe_b200_circuit_destroy", "tfhe_b200_circuit_info", "tfhe_b200_circuit_run",
+    "tfhe_b200_circuit_create", "tfhe_b200_circuit_destroy", "tfhe_b200_circuit_plan", "tfhe_b200_circuit_info", "tfhe_b200_circuit_run",
 ]
 
 
@@ -374,6 +375,22 @@ class Context:
 WIRE_NOT = 0x80000000
 
 GATE_NODE = np.dtype([("op", np.int32), ("a", np.uint32), ("b", np.uint32)])
+
+
+def circuit_plan(gates, n_inputs: int, outputs):
+    """Host-only validation + levelisation of a netlist (tfhe_b200_circuit_plan; needs no GPU).
+    Returns (n_levels, max_level_width, level of every gate); raises TfheB200Error on an invalid netlist."""
+    lib = load_library()
+    g = np.zeros(len(gates), GATE_NODE)
+    for k, (op, a, b) in enumerate(gates):
+        g[k] = (int(op), int(a), int(b))
+    outs = np.ascontiguousarray(outputs, dtype=np.uint32)
+    lv, wd = C.c_size_t(), C.c_size_t()
+    gl = np.zeros(len(g), np.uint32)
+    rc = lib.tfhe_b200_circuit_plan(_ptr(g), len(g), int(n_inputs), _ptr(outs), len(outs), C.byref(lv), C.byref(wd), _ptr(gl))
+    if rc:
+        raise TfheB200Error(rc, "invalid circuit")
+    return lv.value, wd.value, gl
 
 
 class Circuit:

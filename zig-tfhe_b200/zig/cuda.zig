@@ -65,5 +65,7 @@ pub const wire_not: u32 = 0x80000000; // Gates.notGate of the referenced wire, f
 pub const GateNode = extern struct { op: i32, a: u32, b: u32 };
 pub extern fn tfhe_b200_circuit_create(ctx: *Ctx, gates: [*]const GateNode, n_gates: usize, n_inputs: usize, outputs: [*]const u32, n_outputs: usize, out: *?*Circuit) c_int;
 pub extern fn tfhe_b200_circuit_destroy(circuit: ?*Circuit) void;
+/// host-only validation + levelisation (no device needed)
+pub extern fn tfhe_b200_circuit_plan(gates: [*]const GateNode, n_gates: usize, n_inputs: usize, outputs: [*]const u32, n_outputs: usize, n_levels: ?*usize, max_level_width: ?*usize, gate_level: ?[*]u32) c_int;
 pub extern fn tfhe_b200_circuit_info(circuit: *const Circuit, n_levels: ?*usize, max_level_width: ?*usize, n_gates: ?*usize) c_int;
 pub extern fn tfhe_b200_circuit_run(ctx: *Ctx, circuit: *Circuit, inputs: [*]const u32, outputs: [*]u32, instances: usize) c_int;
