@@ -243,3 +243,24 @@ def test_native_circuit_not_folding_and_all_gates_vs_oracle():
             tfhe_b200.Circuit(ctx, [(0, 0, 1)], 2, [9])
     finally:
         ctx.close()
+
+
+@pytest.mark.gpu
+def test_mux_naive_circuit_matches_the_reference_composition():
+    """gates.zig:124-129 and its truth-table test (gates.zig:513-544) as one two-level circuit over all 8 input rows"""
+    import tfhe_b200
+    from tfhe_b200 import circuits
+    orc = O.Oracle("128"); keys = keys_for("128")
+    ctx = tfhe_b200.Context("128", devices=[0])
+    try:
+        ctx.load_key(keys.bsk, keys.ksk, keys.offset)
+        rows = np.array([[a, b, c] for a in (0, 1) for b in (0, 1) for c in (0, 1)], np.uint8)
+        ca = orc.encrypt_bools(rows[:, 0], keys, 41); cb = orc.encrypt_bools(rows[:, 1], keys, 42); cc = orc.encrypt_bools(rows[:, 2], keys, 43)
+        out, circ = circuits.mux_naive_batch(ctx, ca, cb, cc)
+        assert circ.levels == 2 and circ.n_gates == 3
+        assert (orc.decrypt_bools(out, keys) == np.where(rows[:, 0] == 1, rows[:, 1], rows[:, 2])).all()
+        ref = np.stack([orc.gate(O.OR, orc.gate(O.AND, ca[i], cb[i], keys), orc.gate(O.AND, orc.gate_not(ca[i]), cc[i], keys), keys) for i in range(8)])
+        assert (out == ref).all()
+        circ.close()
+    finally:
+        ctx.close()

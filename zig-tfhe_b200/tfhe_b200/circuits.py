@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from . import AND, OR, XOR, Circuit, Context
+from . import AND, OR, WIRE_NOT, XOR, Circuit, Context
 
 
 def to_bits(values, width: int) -> np.ndarray:
@@ -119,3 +119,16 @@ def ripple_carry_add_native(ctx: Context, a_bits: np.ndarray, b_bits: np.ndarray
         circuit = Circuit(ctx, gates, n_in, outs)
     out = circuit.run(np.concatenate([a_bits, b_bits, cin[None]]))
     return out[:W], out[W], circuit
+
+
+def mux_naive_netlist():
+    """Gates.muxNaive (gates.zig:124-129): a ? b : c = (a & b) | (~a & c); inputs a, b, c; the NOT is folded into the AND."""
+    return [(AND, 0, 1), (AND, 0 | WIRE_NOT, 2), (OR, 3, 4)], 3, [5]
+
+
+def mux_naive_batch(ctx: Context, a: np.ndarray, b: np.ndarray, c: np.ndarray, circuit: Circuit | None = None):
+    """`count` independent muxNaive evaluations in one circuit call (2 levels, 3 bootstraps each); a, b, c: [count][n+1]."""
+    if circuit is None:
+        gates, n_in, outs = mux_naive_netlist()
+        circuit = Circuit(ctx, gates, n_in, outs)
+    return circuit.run(np.stack([a, b, c]))[0], circuit
