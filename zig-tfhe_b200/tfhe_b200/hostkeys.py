@@ -119,6 +119,21 @@ def gen_key_switching_key(params: Params, sk: SecretKey, rng):
     return ksk.reshape(N * t * base, n + 1)
 
 
+def gen_reencryption_key(params: Params, key_from, key_to, rng, basebit=None, t=None):
+    """proxy_reenc.ProxyReencryptionKey.newSymmetric (proxy_reenc.zig:205-262): entry (i, j, k) encrypts
+    k * key_from[i] / 2^((j+1) basebit) under key_to; [n*t*base][n+1], k = 0 rows left zero (never read)."""
+    basebit = params.basebit if basebit is None else basebit
+    t = params.iks_t if t is None else t
+    base, n = 1 << basebit, params.n
+    a0 = ALPHAS[params.name][0]
+    key = np.zeros((n, t, base, n + 1), np.uint32)
+    for j in range(t):
+        for k in range(1, base):
+            mu = (k * np.asarray(key_from, np.float64)) / float(1 << ((j + 1) * basebit))
+            key[:, j, k, :] = tlwe_encrypt_f64(mu, a0, np.asarray(key_to, np.uint32), rng)
+    return key.reshape(n * t * base, n + 1)
+
+
 def gen_bootstrapping_key(params: Params, sk: SecretKey, rng):
     """key.zig:182-212 (TRGSW(s0_i) in FFT form): f64 [n][2L][2][N]."""
     n, L = params.n, params.L
