@@ -40,6 +40,7 @@ namespace {
 // Teams of two (tuning key "team") cut the shared-memory wavefronts by 11 % (ncu) but the kernel is latency-bound,
 // not shared-memory-bound: 88.8 k vs 90.8 k bootstraps/s at KCT = 4, 83.9 k at KCT = 6 with shared-memory twiddles
 // (profiles/r01_team_probe.log, r01_wave_scaling.log).  The default stays one ciphertext per warp pair, KCT = 4.
+constexpr bool kUnrollL3 = true;   // experiment: L = 3 known at compile time, digit loop fully unrolled
 constexpr int kMaxStages = 4;  // deepest key ring (16 KiB per stage); Layout<KCT>::kStages picks the depth
 
 // Key-ring producer state, live only in thread 0 of the CTA (see header comment).
@@ -226,7 +227,7 @@ struct Layout {
     }
 };
 
-template <int KCT, bool USE_TMA, bool MARGIN, int TEAM = 1>
+template <int KCT, bool USE_TMA, bool MARGIN, int TEAM = 1, int LT = 0>
 __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(const BrArgs P) {
     using Lay = Layout<KCT, TEAM>;
     constexpr int POW = Lay::kTw2Mode, POW3 = Lay::kTw3Mode;
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
     uint64_t *empty_bar = full_bar + kMaxStages;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(ptr + 64);
     ptr += 80;
-    const int n = P.n, L = P.L, bgbit = P.bgbit;
+    const int n = P.n, L = LT > 0 ? LT : P.L, bgbit = LT == 3 ? 6 : P.bgbit;   // LT = 3: the L = 3 / BGBIT = 6 sets (80/110/128-bit)
     static_assert(TEAM == 1 || (TEAM == 2 && KCT % 2 == 0), "a team never straddles CTAs");
     constexpr int kTeamThreads = TEAM * kGroupThreads;
     const int group_bytes = Lay::group_bytes(n);
@@ -351,7 +352,7 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
 
     const uint32_t mask = (1u << bgbit) - 1u, half_bg = 1u << (bgbit - 1);
     const uint32_t offset = P.offset;
-    const int wide = P.wide_round;
+    const int wide = LT == 3 ? 0 : P.wide_round;   // BGBIT = 6: magic-add rounding (coefficients < 2^45)
     int stage = 0;
     uint32_t phase = 0;
     double margin = 0.0;
@@ -378,7 +379,7 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
                 const uint32_t *accp = h ? acc_b : acc_a;
                 uint32_t d[16];
                 load_rot_diffs(d, accp, at, offset, hi, lo);
-#pragma unroll 1
+#pragma unroll (LT > 0 ? LT : 1)
                 for (int l = 0; l < L; l++) {
                     cplx v[8];
                     digits_to_cplx(v, d, 32 - (l + 1) * bgbit, mask, half_bg);
@@ -839,6 +840,7 @@ cudaError_t launch_variant(const BrArgs &a, cudaStream_t s) {
     const int threads = KCT * kGroupThreads;
     const size_t smem = (USE_TMA ? Lay::kStages * kBskChunkBytes : 0) + 80 + Lay::kTwBytes + (size_t)KCT * Lay::group_bytes(a.n);
     auto kern = blind_rotate_kernel<KCT, USE_TMA, MARGIN, TEAM>;
+    if (KCT == 4 && USE_TMA && !MARGIN && a.L == 3 && a.bgbit == 6 && kUnrollL3) kern = blind_rotate_kernel<KCT, USE_TMA, MARGIN, TEAM, (KCT == 4 && USE_TMA && !MARGIN) ? 3 : 0>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const unsigned grid = (a.B + KCT - 1) / KCT;
