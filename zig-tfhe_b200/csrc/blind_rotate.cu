@@ -366,6 +366,10 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
         for (int s = 0; s < kStages; s++) producer_poll(pr);
     }
 
+    // CTAs of one wave start in lock step and would ask L2 for the same 16 KiB key chunk in the same few hundred cycles for
+    // the whole launch (measured: a single wave takes 6.5 ms, the 70th of a long launch 6.1 ms, once the CTAs have drifted
+    // apart).  A few microseconds of per-CTA stagger at the start spreads them from the first step on.
+    if (USE_TMA) __nanosleep((blockIdx.x % 41u) * 128u);
     // ---- n CMUX steps (trgsw.zig:311-330)
     for (int i = 0; i < n; i++) {
         const int at = atil[i];
@@ -891,7 +895,7 @@ cudaError_t launch_blind_rotate(const BrArgs &a, const BrTuning &tune, bool trac
         const unsigned wave = sm_total * 4;
         const unsigned full = (a.B / wave) * wave, tail = a.B - full;
         if (full > 0 && tail > 0) {
-            static const double t_cta[5] = {0.0, 4.5, 4.5, 6.1, 6.5};
+            static const double t_cta[5] = {0.0, 4.6, 4.6, 6.1, 6.15};
             double best_tail = 1e30;
             for (int k = 1; k <= 4; k++) best_tail = std::min(best_tail, ((tail + sm_total * k - 1) / (sm_total * k)) * t_cta[k]);
             if (tune.latency_mode != 0 && tail <= sm_total && !a.wide_round) best_tail = std::min(best_tail, 2.5);
@@ -910,9 +914,9 @@ cudaError_t launch_blind_rotate(const BrArgs &a, const BrTuning &tune, bool trac
     }
     if (kct <= 0) {
         // minimise (number of CTA waves) x (time of one CTA at that width); CTA times measured on B200 at n = 700
-        // (profiles/r01_first_light*.log, profiles/r01_wave_scaling.log): 1 or 2 ciphertexts 4.5 ms, 3: 6.1 ms, 4: 6.5 ms.
+        // (profiles/r01_first_light*.log, profiles/r01_wave_scaling.log): 1 or 2 ciphertexts 4.6 ms, 3: 6.1 ms, 4: 6.15 ms.
         // (6 with teams of two and shared-memory twiddles: 10.6 ms -- 84 k/s against 91 k/s at 4, so never chosen.)
-        static const double t_cta[5] = {0.0, 4.5, 4.5, 6.1, 6.5};
+        static const double t_cta[5] = {0.0, 4.6, 4.6, 6.1, 6.15};
         const unsigned sms = tune.sm_count > 0 ? (unsigned)tune.sm_count : 148u;
         double best = 1e30;
         for (int k = 1; k <= 4; k++) {
