@@ -844,7 +844,10 @@ cudaError_t launch_variant(const BrArgs &a, cudaStream_t s) {
     const int threads = KCT * kGroupThreads;
     const size_t smem = (USE_TMA ? Lay::kStages * kBskChunkBytes : 0) + 80 + Lay::kTwBytes + (size_t)KCT * Lay::group_bytes(a.n);
     auto kern = blind_rotate_kernel<KCT, USE_TMA, MARGIN, TEAM>;
-    if (KCT == 4 && USE_TMA && !MARGIN && a.L == 3 && a.bgbit == 6 && kUnrollL3) kern = blind_rotate_kernel<KCT, USE_TMA, MARGIN, TEAM, (KCT == 4 && USE_TMA && !MARGIN) ? 3 : 0>;
+    // the L = 3 / BGBIT = 6 sets (80/110/128-bit) get their own instantiation: digit loop unrolled, shifts, masks and the
+    // rounding mode compile-time (+5 % on the 128-bit bench; profiles/r01_wave_scaling.log)
+    if (KCT <= 4 && USE_TMA && !MARGIN && a.L == 3 && a.bgbit == 6 && !a.wide_round && kUnrollL3)
+        kern = blind_rotate_kernel<KCT, USE_TMA, MARGIN, TEAM, (KCT <= 4 && USE_TMA && !MARGIN) ? 3 : 0>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const unsigned grid = (a.B + KCT - 1) / KCT;
