@@ -40,7 +40,7 @@ namespace {
 // Teams of two (tuning key "team") cut the shared-memory wavefronts by 11 % (ncu) but the kernel is latency-bound,
 // not shared-memory-bound: 88.8 k vs 90.8 k bootstraps/s at KCT = 4, 83.9 k at KCT = 6 with shared-memory twiddles
 // (profiles/r01_team_probe.log, r01_wave_scaling.log).  The default stays one ciphertext per warp pair, KCT = 4.
-constexpr bool kUnrollL3 = true;   // experiment: L = 3 known at compile time, digit loop fully unrolled
+constexpr bool kUnrollL3 = true;   // L = 3 / BGBIT = 6 instantiation of the throughput kernel (false: generic kernel only, for A/B runs)
 constexpr int kMaxStages = 4;  // deepest key ring (16 KiB per stage); Layout<KCT>::kStages picks the depth
 
 // Key-ring producer state, live only in thread 0 of the CTA (see header comment).
@@ -677,7 +677,7 @@ __global__ void __launch_bounds__(L * kGroupThreads, 1) blind_rotate_pair_kernel
     uint16_t *atil = reinterpret_cast<uint16_t *>(xbase + L * kXBytes + 64);
     // Key rows are double-buffered: the row of step i + 1 is requested at the top of step i (its buffer held the products
     // of step i - 1, all consumed before that step's cluster barrier), so the bulk copy has a whole step to land.
-    const int n = P.n, bgbit = P.bgbit;
+    const int n = P.n, bgbit = L == 3 ? 6 : P.bgbit;   // the launcher routes L = 3 here only with BGBIT = 6
     const int tid = threadIdx.x, g = tid >> 6, t = tid & 63, hi = t >> 3, lo = t & 7;
     const int barid = 1 + g;
     const uint32_t h = cluster_ctarank();            // which polynomial of the accumulator this CTA owns
@@ -728,7 +728,7 @@ __global__ void __launch_bounds__(L * kGroupThreads, 1) blind_rotate_pair_kernel
 
     const uint32_t mask = (1u << bgbit) - 1u, half_bg = 1u << (bgbit - 1);
     const int sh = 32 - (g + 1) * bgbit;
-    const int wide = P.wide_round;
+    const int wide = L == 3 ? 0 : P.wide_round;
     double margin = 0.0;
     Producer pr;
     pr.active = false; pr.remaining = 0;
@@ -873,7 +873,7 @@ cudaError_t launch_blind_rotate(const BrArgs &a, const BrTuning &tune, bool trac
     const unsigned sm_total = tune.sm_count > 0 ? (unsigned)tune.sm_count : 148u;
     // latency mode: every ciphertext gets an SM of its own; only where the external product is exact
     // (so the different summation order cannot change a rounded coefficient)
-    if (tune.latency_mode == 1 && tune.kct <= 0 && 2 * a.B <= sm_total && !a.wide_round && !track_margin && a.L >= 1 && a.L <= 3) {
+    if (tune.latency_mode == 1 && tune.kct <= 0 && 2 * a.B <= sm_total && !a.wide_round && !track_margin && a.L >= 1 && a.L <= 3 && (a.L != 3 || a.bgbit == 6)) {
         if (launches) (*launches)++;     // one ciphertext per pair of SMs
         switch (a.L) {
             case 1: return launch_pair<1>(a, s);
@@ -898,7 +898,7 @@ cudaError_t launch_blind_rotate(const BrArgs &a, const BrTuning &tune, bool trac
         const unsigned wave = sm_total * 4;
         const unsigned full = (a.B / wave) * wave, tail = a.B - full;
         if (full > 0 && tail > 0) {
-            static const double t_cta[5] = {0.0, 4.6, 4.6, 6.1, 6.15};
+            static const double t_cta[5] = {0.0, 4.6, 4.6, 5.8, 6.15};
             double best_tail = 1e30;
             for (int k = 1; k <= 4; k++) best_tail = std::min(best_tail, ((tail + sm_total * k - 1) / (sm_total * k)) * t_cta[k]);
             if (tune.latency_mode != 0 && tail <= sm_total && !a.wide_round) best_tail = std::min(best_tail, 2.5);
@@ -917,9 +917,9 @@ cudaError_t launch_blind_rotate(const BrArgs &a, const BrTuning &tune, bool trac
     }
     if (kct <= 0) {
         // minimise (number of CTA waves) x (time of one CTA at that width); CTA times measured on B200 at n = 700
-        // (profiles/r01_first_light*.log, profiles/r01_wave_scaling.log): 1 or 2 ciphertexts 4.6 ms, 3: 6.1 ms, 4: 6.15 ms.
+        // (profiles/r01_first_light*.log, profiles/r01_wave_scaling.log): 1 or 2 ciphertexts 4.6 ms, 3: 5.8 ms, 4: 6.15 ms.
         // (6 with teams of two and shared-memory twiddles: 10.6 ms -- 84 k/s against 91 k/s at 4, so never chosen.)
-        static const double t_cta[5] = {0.0, 4.6, 4.6, 6.1, 6.15};
+        static const double t_cta[5] = {0.0, 4.6, 4.6, 5.8, 6.15};
         const unsigned sms = tune.sm_count > 0 ? (unsigned)tune.sm_count : 148u;
         double best = 1e30;
         for (int k = 1; k <= 4; k++) {
