@@ -203,9 +203,12 @@ int tfhe_b200_track_margin(tfhe_b200_ctx *ctx, int enable);
 double tfhe_b200_max_round_margin(tfhe_b200_ctx *ctx, int reset);
 /* number of kernels this library launched since the context was created (bench `gpu_launches`) */
 uint64_t tfhe_b200_launch_count(const tfhe_b200_ctx *ctx);
-/* tuning knobs (tests/bench): "kct" ciphertexts per CTA of the blind-rotation kernel (0 = default),
- * "use_tma" 0/1, "max_chunk" ciphertexts per launch, "timing" 0/1 (record CUDA events around K1/K2),
- * "team" (2: two ciphertexts per warp, a measured K1 variant kept for A/B runs), "circuit_graph" 0/1 (CUDA-graph replay of circuit levels) */
+/* tuning knobs (tests/bench): "kct" ciphertexts per CTA of the blind-rotation kernel (0 = automatic: whole waves at 4 plus a
+ * separately sized tail launch), "use_tma" 0/1, "latency_mode" (1 = automatic: batches <= SMs/2 on two-CTA clusters, <= SMs
+ * on one CTA per ciphertext; 2 = never the cluster kernel; 0 = throughput kernel only), "team" (2: two ciphertexts per
+ * warp, a measured K1 variant kept for A/B runs), "max_chunk" ciphertexts per launch, "timing" 0/1 (record CUDA events
+ * around K1/K2), "ks_tile" / "ks_vec" key-switch tile shape, "circuit_graph" 0/1 (CUDA-graph replay of circuit levels),
+ * "circuit_lanes" concurrent instance groups per device (read at circuit_create; default 4) */
 int tfhe_b200_set_tuning(tfhe_b200_ctx *ctx, const char *key, int value);
 /* with "timing" on: device time in ms of the last blind-rotation (which = 0) or key-switch (which = 1)
  * kernel enqueued on device `dev`, measured with CUDA events on the launching stream */
