@@ -56,7 +56,8 @@ typedef enum {
     TFHE_B200_ERR_NO_DEVICE = 2,   /* no CUDA device, or device is not sm_100 */
     TFHE_B200_ERR_CUDA = 3,        /* CUDA runtime error (see last_error) */
     TFHE_B200_ERR_NO_KEY = 4,      /* hot-path call before load_key */
-    TFHE_B200_ERR_NOT_IMPLEMENTED = 5
+    TFHE_B200_ERR_NOT_IMPLEMENTED = 5,
+    TFHE_B200_ERR_IO = 6           /* cloud-key file cannot be opened / read / written */
 } tfhe_b200_status;
 
 /* gate opcodes: the ten bootstrapped two-input gates of Gates (src/gates.zig:48-121) */
@@ -108,6 +109,34 @@ int tfhe_b200_load_key_device(tfhe_b200_ctx *ctx, int dev, const double *d_bsk, 
  * at the top of this file, e.g. to hand the same CloudKey to the CPU implementation or to serialise it. */
 int tfhe_b200_keygen(tfhe_b200_ctx *ctx, const uint32_t *key_lv0, const uint32_t *key_lv1, uint64_t seed, double ksk_alpha,
                      double bsk_alpha, double *bsk_out, uint32_t *ksk_out);
+/* ---- flat cloud-key file ----------------------------------------------------------------
+ * key.CloudKey (src/key.zig:61-65) has no serialised form in the reference and every test run regenerates it (~30 s,
+ * src/key.zig:240).  File format, little endian, version 1:
+ *   0    char[8]  "TFHEB2CK"          8   u32 version (1)           12  u32 header_bytes (4096)
+ *   16   i32[6]   n, N, L, bgbit, basebit, iks_t (tfhe_b200_params)
+ *   40   u32 decomposition_offset     44  u32 flags (bit 0: key-switching key present)
+ *   48   u64 bsk_offset (4096), u64 bsk_bytes, u64 ksk_offset (4096-aligned), u64 ksk_bytes
+ *   80   u64 bsk_checksum, u64 ksk_checksum       96  u64 header_checksum (over bytes 0..96)
+ *   then zero padding; the two sections are CloudKey.bootstrapping_key and CloudKey.key_switching_key exactly as laid
+ *   out at the top of this header (packed KSK rows), so a host can mmap the file and use the sections in place.
+ *   checksum(data): four FNV-1a-64 lanes (basis 0xcbf29ce484222325 + lane, prime 0x100000001b3) over the little-endian
+ *   64-bit words of data, word i into lane i mod 4 (a trailing partial word zero-extended); then h = basis; for each lane
+ *   h = (h ^ lane) * prime; result (h ^ byte_length) * prime.
+ * To save a generated key: tfhe_b200_keygen(..., bsk_out, ksk_out) then tfhe_b200_key_file_write.
+ * The three key_file_* calls are host-only (no context, no device); errors: TFHE_B200_ERR_IO / _INVALID, text in
+ * tfhe_b200_key_file_last_error() (thread local).  write() goes through a temporary + rename. */
+int tfhe_b200_key_file_write(const char *path, const tfhe_b200_params *params, const double *bsk, const uint32_t *ksk /* or NULL */,
+                             uint32_t decomposition_offset);
+/* header only (no payload checksum pass); any out pointer may be NULL; ksk_bytes == 0: file has no key-switching key */
+int tfhe_b200_key_file_info(const char *path, tfhe_b200_params *params, uint32_t *decomposition_offset, uint64_t *bsk_bytes,
+                            uint64_t *ksk_bytes);
+/* verifies both checksums, then copies the sections out (either pointer may be NULL) */
+int tfhe_b200_key_file_read(const char *path, double *bsk, uint32_t *ksk);
+const char *tfhe_b200_key_file_last_error(void);
+/* tfhe_b200_load_key straight from a file: mmap, verify header + checksums, parameter set must equal the context's,
+ * upload to every device of the context */
+int tfhe_b200_load_key_file(tfhe_b200_ctx *ctx, const char *path);
+
 /* CloudKey.decomposition_offset of the loaded / generated key (key.genDecompositionOffset, src/key.zig:121-131) */
 uint32_t tfhe_b200_decomposition_offset(const tfhe_b200_ctx *ctx);
 int tfhe_b200_set_mode(tfhe_b200_ctx *ctx, int mode);

@@ -53,6 +53,11 @@ int main(int argc, char **argv) {
         std::fwrite(sum_carry.data(), 4, sum_carry.size(), f);
         std::fclose(f);
         if (adder.levels() != 3 || adder.gates() != 5) return 5;
+        // CloudKey -> flat file -> a second evaluator built from the file alone: same ciphertext bits
+        const std::string key_path = dir + "/cloud.key";
+        tfhe_b200::saveCloudKey(key_path, p, tfhe_b200::CloudKey{0x82080000u, bsk.data(), ksk.data()});
+        tfhe_b200::GpuBootstrap from_file(p, key_path);
+        if (from_file.bootstrap(in[0].first) != boot) return 6;
         std::printf("ok strategy=%s count=%zu\n", gates.bootstrapStrategy(), count);
     } catch (const tfhe_b200::Error &e) {
         std::printf("error %d: %s\n", e.code, e.what());

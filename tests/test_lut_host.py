@@ -48,6 +48,34 @@ def test_bootstrap_lut_on_gpu():
         c.close()
 
 
+def test_reference_generator_and_encoder_tests_mirrored():
+    """lut/generator.zig:259-345 and lut/encoder.zig tests, same cases, plus what they leave unchecked"""
+    from tfhe_b200 import lut
+    g = lut.Generator(2)
+    assert (g.encoder.message_modulus, g.poly_degree, g.lookup_table_size) == (2, 1024, 1024)      # "generator creation"
+    for f in (lambda x: x, lambda x: 1 - x, lambda x: 1):                                          # identity / not / constant
+        assert not g.generate_lookup_table(f).is_empty()
+    assert not lut.Generator(4).generate_lookup_table(lambda x: (x + 1) % 4).is_empty()            # "4bit function"
+    half = lut.Generator(2, 0.5)                                                                   # "custom scale"
+    t = half.generate_lookup_table(lambda x: x)
+    assert not t.is_empty()
+    # message 1 at scale 0.5 is torus 1/2: windows [256, 768) hold 0x80000000, the rest 0 (and -0 = 0 in the tail)
+    assert set(np.unique(t.poly[1]).tolist()) == {0, 0x80000000} and not t.poly[0].any()
+    for x in (0, 0xFFFFFFFF // 2, 0xFFFFFFFF):                                                     # "mod switch"
+        assert 0 <= g.mod_switch(x) < g.lookup_table_size
+    assert g.mod_switch(0) == 0 and g.mod_switch(0xFFFFFFFF // 2) == 512
+    # generateLookupTableCustom (generator.zig:202-212) = a generator with Encoder.withScale(modulus, scale)
+    c = g.generate_lookup_table_custom(lambda x: (x + 1) % 4, 4, 0.125)
+    assert (c.poly == lut.Generator(4).generate_lookup_table(lambda x: (x + 1) % 4).poly).all()   # 0.125 = default scale of modulus 4
+    assert (g.generate_lookup_table_custom(lambda x: x, 2, 0.5).poly == t.poly).all()
+    # encodeWithScale (encoder.zig:83-87)
+    e = lut.Encoder(4)
+    assert e.encode_with_scale(3, 0.125) == e.encode(3) == 0x60000000 and e.encode_with_scale(5, 0.25) == 0x40000000
+    assert e.decode_bool(e.encode(0)) is False and e.decode_bool(e.encode(2)) is True
+    # the compact table form the device generator consumes
+    assert (lut.Generator(4).function_table(lambda x: 3 - x) == [0x60000000, 0x40000000, 0x20000000, 0]).all()
+
+
 @pytest.mark.gpu
 def test_device_lut_generator_and_table_bootstrap():
     """tfhe_b200_lut_generate == the host mirror == the oracle for every modulus (incl. non powers of two), and

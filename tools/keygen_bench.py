@@ -23,5 +23,18 @@ for export in (False, True, False):
     ctx.sync()
     dt = time.perf_counter() - t0
     print(f"device keygen (export to host = {export}): {dt * 1e3:.1f} ms", flush=True)
+# flat cloud-key file: write, then a fresh context loads it (mmap + checksum + upload + re-layout)
+import tempfile  # noqa: E402
+ck = ctx.keygen(keys.s0, keys.s1, seed=7, ksk_alpha=a0, bsk_alpha=a1, export=True)
+with tempfile.TemporaryDirectory(dir=os.environ.get("KEYFILE_DIR")) as tmp:
+    path = os.path.join(tmp, "cloud128.key")
+    t0 = time.perf_counter(); ck.save(path, "128"); t_save = time.perf_counter() - t0
+    ctx2 = tfhe_b200.Context(params, devices=[0])
+    for _ in range(2):
+        t0 = time.perf_counter(); ctx2.load_key_file(path); ctx2.sync(); t_load = time.perf_counter() - t0
+        print(f"key file ({os.path.getsize(path) / 1e6:.1f} MB): save {t_save * 1e3:.0f} ms, load_key_file {t_load * 1e3:.0f} ms", flush=True)
+    t0 = time.perf_counter(); ctx2.load_key(ck.bootstrapping_key, ck.key_switching_key, ck.decomposition_offset); ctx2.sync()
+    print(f"load_key from host arrays: {(time.perf_counter() - t0) * 1e3:.0f} ms")
+    ctx2.close()
 print(f"numpy host mirror: {t_host:.2f} s; C++ oracle (all host threads): {t_orc:.2f} s; reference (key.zig:240 comment): ~30 s")
 ctx.close()

@@ -16,6 +16,7 @@
 #include "../../include/tfhe_b200.h"
 #include "host_tables.h"
 #include "kernels.cuh"
+#include "key_file.h"
 
 using namespace tfhe_b200;
 
@@ -436,6 +437,22 @@ int tfhe_b200_load_key(tfhe_b200_ctx *c, const double *bsk, const uint32_t *ksk,
     c->has_key = true;
     c->has_ksk = ksk != nullptr;
     return 0;
+}
+
+int tfhe_b200_load_key_file(tfhe_b200_ctx *c, const char *path) {
+    if (!c || !path) return fail(c, TFHE_B200_ERR_INVALID, "null argument");
+    char msg[512];
+    tfhe_b200_keyfile::View v;
+    if (int r = tfhe_b200_keyfile::map(path, true, v, msg, sizeof msg)) return fail(c, r, "%s", msg);
+    const tfhe_b200_params &f = v.header.params, &p = c->prm;
+    int rc;
+    if (f.n != p.n || f.N != p.N || f.L != p.L || f.bgbit != p.bgbit || f.basebit != p.basebit || f.iks_t != p.iks_t)
+        rc = fail(c, TFHE_B200_ERR_INVALID, "%s: key is for n=%d L=%d bgbit=%d basebit=%d t=%d, the context for n=%d L=%d bgbit=%d basebit=%d t=%d",
+                  path, f.n, f.L, f.bgbit, f.basebit, f.iks_t, p.n, p.L, p.bgbit, p.basebit, p.iks_t);
+    else
+        rc = tfhe_b200_load_key(c, v.bsk, v.ksk, 0, v.header.decomposition_offset);
+    tfhe_b200_keyfile::unmap(v);
+    return rc;
 }
 
 int tfhe_b200_load_key_device(tfhe_b200_ctx *c, int dev, const double *d_bsk, const uint32_t *d_ksk, uint32_t offset) {

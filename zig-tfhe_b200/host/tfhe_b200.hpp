@@ -40,6 +40,12 @@ struct CloudKey {
     const uint32_t *key_switching_key;      // [N*t*base][n+1] or nullptr (CloudKey.newNoKsk, key.zig:80-100)
 };
 
+// CloudKey <-> flat file; host only
+inline void saveCloudKey(const std::string &path, const tfhe_b200_params &p, const CloudKey &ck) {
+    if (int rc = tfhe_b200_key_file_write(path.c_str(), &p, ck.bootstrapping_key, ck.key_switching_key, ck.decomposition_offset))
+        throw Error(rc, tfhe_b200_key_file_last_error());
+}
+
 class GpuBootstrap {
 public:
     GpuBootstrap(const tfhe_b200_params &p, const CloudKey &ck, const std::vector<int> &devices = {0}) : words_(p.n + 1) {
@@ -55,6 +61,13 @@ public:
         int rc = tfhe_b200_create(&p, devices.data(), (int)devices.size(), &ctx_);
         if (rc) throw Error(rc, "no sm_100 CUDA device / bad parameters");
         check(tfhe_b200_keygen(ctx_, key_lv0, key_lv1, seed, ksk_alpha, bsk_alpha, nullptr, nullptr));
+    }
+    // from a flat cloud-key file (include/tfhe_b200.h "flat cloud-key file"): mmap + checksum + upload, no 30 s key generation
+    // per run (key.zig:240)
+    GpuBootstrap(const tfhe_b200_params &p, const std::string &key_file, const std::vector<int> &devices = {0}) : words_(p.n + 1) {
+        int rc = tfhe_b200_create(&p, devices.data(), (int)devices.size(), &ctx_);
+        if (rc) throw Error(rc, "no sm_100 CUDA device / bad parameters");
+        check(tfhe_b200_load_key_file(ctx_, key_file.c_str()));
     }
     GpuBootstrap(const GpuBootstrap &) = delete;
     GpuBootstrap &operator=(const GpuBootstrap &) = delete;

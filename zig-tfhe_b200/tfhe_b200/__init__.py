@@ -32,7 +32,7 @@ GATE_NAMES = ["nand", "or", "and", "xor", "xnor", "nor", "andny", "andyn", "orny
 MODE_FAST, MODE_EXACT = 0, 1
 N = 1024
 
-STATUS = {0: "ok", 1: "invalid argument", 2: "no sm_100 CUDA device", 3: "CUDA error", 4: "no key loaded", 5: "not implemented"}
+STATUS = {0: "ok", 1: "invalid argument", 2: "no sm_100 CUDA device", 3: "CUDA error", 4: "no key loaded", 5: "not implemented", 6: "I/O error"}
 
 
 class TfheB200Error(RuntimeError):
@@ -128,6 +128,11 @@ def load_library():
         "tfhe_b200_circuit_plan": (i32, [vp, sz, sz, vp, sz, vp, vp, vp]),
         "tfhe_b200_circuit_info": (i32, [vp, vp, vp, vp]),
         "tfhe_b200_circuit_run": (i32, [vp, vp, vp, vp, sz]),
+        "tfhe_b200_key_file_write": (i32, [C.c_char_p, vp, vp, vp, u32]),
+        "tfhe_b200_key_file_info": (i32, [C.c_char_p, vp, vp, vp, vp]),
+        "tfhe_b200_key_file_read": (i32, [C.c_char_p, vp, vp]),
+        "tfhe_b200_key_file_last_error": (C.c_char_p, []),
+        "tfhe_b200_load_key_file": (i32, [vp, C.c_char_p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)   # AttributeError if the library does not export a declared symbol
@@ -148,6 +153,8 @@ EXPORTED_SYMBOLS = [
     "tfhe_b200_load_reencryption_key", "tfhe_b200_reencrypt_batch",
     "tfhe_b200_keygen", "tfhe_b200_decomposition_offset", "tfhe_b200_lut_bootstrap_batch", "tfhe_b200_lut_generate",
     "tfhe_b200_circuit_create", "tfhe_b200_circuit_destroy", "tfhe_b200_circuit_plan", "tfhe_b200_circuit_info", "tfhe_b200_circuit_run",
+    "tfhe_b200_key_file_write", "tfhe_b200_key_file_info", "tfhe_b200_key_file_read", "tfhe_b200_key_file_last_error",
+    "tfhe_b200_load_key_file",
 ]
 
 
@@ -173,6 +180,53 @@ class CloudKey:
     key_switching_key: np.ndarray | None     # u32 [N*t*base][n+1]
     decomposition_offset: int
     blind_rotate_testvec: np.ndarray | None = None   # u32 [2][N]; None = key.genTestvec default
+
+    # flat cloud-key file (include/tfhe_b200.h "flat cloud-key file"); host only, no device needed
+    def save(self, path, params: "str | Params"):
+        key_file_write(path, params, self.bootstrapping_key, self.key_switching_key, self.decomposition_offset)
+
+    @staticmethod
+    def load(path) -> "CloudKey":
+        return key_file_read(path)[1]
+
+
+def _kf_check(lib, rc):
+    if rc != 0:
+        raise TfheB200Error(rc, (lib.tfhe_b200_key_file_last_error() or b"").decode())
+
+
+def key_file_write(path, params: "str | Params", bsk, ksk, offset: int):
+    lib = load_library()
+    p = PARAM_SETS[params] if isinstance(params, str) else params
+    cp = _Params(p.n, p.N, p.L, p.bgbit, p.basebit, p.iks_t)
+    bsk = np.ascontiguousarray(bsk, dtype=np.float64)
+    if bsk.size != p.n * 2 * p.L * 2 * N:
+        raise ValueError("bootstrapping key has the wrong size")
+    if ksk is not None:
+        ksk = _u32(ksk)
+        if ksk.size != N * p.iks_t * (1 << p.basebit) * (p.n + 1):
+            raise ValueError("key-switching key has the wrong size")
+    _kf_check(lib, lib.tfhe_b200_key_file_write(os.fsencode(path), C.byref(cp), _ptr(bsk), _ptr(ksk), int(offset) & 0xFFFFFFFF))
+
+
+def key_file_info(path):
+    """(Params, decomposition_offset, bsk_bytes, ksk_bytes) from the header alone"""
+    lib = load_library()
+    cp = _Params(); off = C.c_uint32(); nb = C.c_uint64(); nk = C.c_uint64()
+    _kf_check(lib, lib.tfhe_b200_key_file_info(os.fsencode(path), C.byref(cp), C.byref(off), C.byref(nb), C.byref(nk)))
+    name = next((k for k, q in PARAM_SETS.items()
+                 if (q.n, q.N, q.L, q.bgbit, q.basebit, q.iks_t) == (cp.n, cp.N, cp.L, cp.bgbit, cp.basebit, cp.iks_t)), "custom")
+    return Params(name, cp.n, cp.L, cp.bgbit, cp.basebit, cp.iks_t, cp.N), off.value, nb.value, nk.value
+
+
+def key_file_read(path):
+    """(Params, CloudKey) with both checksums verified"""
+    lib = load_library()
+    p, off, _, nk = key_file_info(path)
+    bsk = np.empty((p.n, 2 * p.L, 2, N), np.float64)
+    ksk = np.empty((N * p.iks_t * (1 << p.basebit), p.n + 1), np.uint32) if nk else None
+    _kf_check(lib, lib.tfhe_b200_key_file_read(os.fsencode(path), _ptr(bsk), _ptr(ksk)))
+    return p, CloudKey(bsk, ksk, off)
 
 
 class Context:
@@ -236,6 +290,10 @@ class Context:
         self._check(self.lib.tfhe_b200_keygen(self.h, _ptr(s0), _ptr(s1), int(seed) & 0xFFFFFFFFFFFFFFFF, float(ksk_alpha), float(bsk_alpha),
                                               _ptr(bsk), _ptr(ksk)))
         return CloudKey(bsk, ksk, int(self.lib.tfhe_b200_decomposition_offset(self.h))) if export else None
+
+    def load_key_file(self, path):
+        """load_key straight from a flat cloud-key file (mmap + checksum + upload), see key_file_write"""
+        self._check(self.lib.tfhe_b200_load_key_file(self.h, os.fsencode(path)))
 
     def load_key_device(self, dev: int, d_bsk: int, d_ksk: int | None, offset: int):
         self._check(self.lib.tfhe_b200_load_key_device(self.h, dev, _ptr(d_bsk), _ptr(d_ksk), int(offset) & 0xFFFFFFFF))

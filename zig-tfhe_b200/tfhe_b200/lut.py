@@ -25,6 +25,9 @@ class Encoder:
     def encode(self, message: int) -> int:                                                   # encoder.zig:66-73
         return int(f64_to_torus(np.float64((message % self.message_modulus) * self.scale)))
 
+    def encode_with_scale(self, message: int, scale: float) -> int:                          # encoder.zig:83-87
+        return int(f64_to_torus(np.float64((message % self.message_modulus) * float(scale))))
+
     def decode(self, value: int) -> int:                                                     # encoder.zig:96-105
         f = float(int(value) & 0xFFFFFFFF) / 4294967296.0
         return int(f / self.scale + 0.5) % self.message_modulus
@@ -67,6 +70,15 @@ class Generator:
     def generate_lookup_table_full(self, f) -> LookupTable:
         """generator.zig:150-191: f returns raw torus values"""
         return self._generate([int(f(x)) & 0xFFFFFFFF for x in range(self.encoder.message_modulus)])
+
+    def generate_lookup_table_custom(self, f, message_modulus: int, scale: float) -> LookupTable:
+        """generator.zig:202-212: the same generator with a temporary Encoder.withScale(message_modulus, scale)"""
+        return Generator(message_modulus, scale).generate_lookup_table(f)
+
+    def function_table(self, f) -> np.ndarray:
+        """`message_modulus` torus words Encoder.encode(f(x)): the compact form tfhe_b200_lut_bootstrap_batch /
+        tfhe_b200_lut_generate take (the LookupTable itself is then built on the device, generator.zig:150-191)"""
+        return np.array([self.encoder.encode(f(x)) for x in range(self.encoder.message_modulus)], np.uint32)
 
     def _generate(self, encoded) -> LookupTable:
         m, size = self.encoder.message_modulus, self.lookup_table_size

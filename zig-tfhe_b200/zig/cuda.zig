@@ -21,7 +21,7 @@ pub const Status = enum(c_int) { ok = 0, invalid = 1, no_device = 2, cuda = 3, n
 
 pub const Gate = enum(c_int) { nand = 0, @"or" = 1, @"and" = 2, xor = 3, xnor = 4, nor = 5, andny = 6, andyn = 7, orny = 8, oryn = 9 };
 
-pub const Error = error{ InvalidArgument, NoDevice, CudaFailure, NoKey, NotImplemented };
+pub const Error = error{ InvalidArgument, NoDevice, CudaFailure, NoKey, NotImplemented, KeyFileIo };
 
 pub fn check(rc: c_int) Error!void {
     return switch (rc) {
@@ -30,6 +30,7 @@ pub fn check(rc: c_int) Error!void {
         2 => Error.NoDevice,
         4 => Error.NoKey,
         5 => Error.NotImplemented,
+        6 => Error.KeyFileIo,
         else => Error.CudaFailure,
     };
 }
@@ -41,6 +42,12 @@ pub extern fn tfhe_b200_num_devices(ctx: ?*const Ctx) c_int;
 pub extern fn tfhe_b200_load_key(ctx: *Ctx, bsk: [*]const f64, ksk: ?[*]const u32, ksk_row_stride_bytes: usize, decomposition_offset: u32) c_int;
 /// key.CloudKey.new on the device from the host-held secret key (key_lv0: [n]u32, key_lv1: [N]u32); bsk_out / ksk_out optional
 pub extern fn tfhe_b200_keygen(ctx: *Ctx, key_lv0: [*]const u32, key_lv1: [*]const u32, seed: u64, ksk_alpha: f64, bsk_alpha: f64, bsk_out: ?[*]f64, ksk_out: ?[*]u32) c_int;
+/// flat cloud-key file (format in include/tfhe_b200.h); the key_file_* calls are host only
+pub extern fn tfhe_b200_key_file_write(path: [*:0]const u8, params: *const Params, bsk: [*]const f64, ksk: ?[*]const u32, decomposition_offset: u32) c_int;
+pub extern fn tfhe_b200_key_file_info(path: [*:0]const u8, params: ?*Params, decomposition_offset: ?*u32, bsk_bytes: ?*u64, ksk_bytes: ?*u64) c_int;
+pub extern fn tfhe_b200_key_file_read(path: [*:0]const u8, bsk: ?[*]f64, ksk: ?[*]u32) c_int;
+pub extern fn tfhe_b200_key_file_last_error() [*:0]const u8;
+pub extern fn tfhe_b200_load_key_file(ctx: *Ctx, path: [*:0]const u8) c_int;
 pub extern fn tfhe_b200_decomposition_offset(ctx: *const Ctx) u32;
 pub extern fn tfhe_b200_set_mode(ctx: *Ctx, mode: c_int) c_int;
 pub extern fn tfhe_b200_gate_batch(ctx: *Ctx, op: c_int, a: [*]const u32, b: [*]const u32, out: [*]u32, count: usize) c_int;
