@@ -751,17 +751,16 @@ __global__ void __launch_bounds__(L * kGroupThreads, 1) blind_rotate_pair_kernel
         }
         fwd_transform<false, false, kTwFull, kTwFull>(v, xb, tw2, tw3, hi, lo, barid, pr);
         mbar_wait(&key_bar[(i & 1) * L + g], (uint32_t)((i >> 1) & 1));
+        // products for the OTHER CTA's output first: their sum is on its way through distributed shared memory (the slowest
+        // hop of the step) while every group multiplies for this CTA's own output
+        const uint32_t other = h ^ 1u;
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
-            my_red[bsk_slot(0, q, t)] = cmul(v[q], my_red[bsk_slot(0, q, t)]);
-            my_red[bsk_slot(1, q, t)] = cmul(v[q], my_red[bsk_slot(1, q, t)]);
-        }
+        for (int q = 0; q < 8; q++) my_red[bsk_slot(other, q, t)] = cmul(v[q], my_red[bsk_slot(other, q, t)]);
         if (tid == 0) mbar_arrive_expect_tx(&recv_bar[i & 1], kHalfN * 16);   // this step's 8 KiB from the partner
         __syncthreads();
         cplx o[8];
         // the partial sum of the OTHER output goes to the partner (group L - 1), our own stays in registers (group 0)
         if (g == L - 1) {
-            const uint32_t other = h ^ 1u;
 #pragma unroll
             for (int q = 0; q < 8; q++) o[q] = red[other * 512 + q * 64 + t];
 #pragma unroll
@@ -773,6 +772,9 @@ __global__ void __launch_bounds__(L * kGroupThreads, 1) blind_rotate_pair_kernel
 #pragma unroll
             for (int q = 0; q < 8; q++) st_async_cplx(dst + q * 64 * 16, o[q], remote_bar + (uint32_t)((i & 1) * 8));
         }
+#pragma unroll
+        for (int q = 0; q < 8; q++) my_red[bsk_slot(h, q, t)] = cmul(v[q], my_red[bsk_slot(h, q, t)]);
+        __syncthreads();
         if (g == 0) {
 #pragma unroll
             for (int q = 0; q < 8; q++) o[q] = red[h * 512 + q * 64 + t];
