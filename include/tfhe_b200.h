@@ -236,7 +236,8 @@ uint64_t tfhe_b200_launch_count(const tfhe_b200_ctx *ctx);
  * separately sized tail launch), "use_tma" 0/1, "latency_mode" (1 = automatic: batches <= SMs/2 on two-CTA clusters, <= SMs
  * on one CTA per ciphertext; 2 = never the cluster kernel; 0 = throughput kernel only), "team" (2: two ciphertexts per
  * warp, a measured K1 variant kept for A/B runs), "max_chunk" ciphertexts per launch, "timing" 0/1 (record CUDA events
- * around K1/K2), "ks_tile" / "ks_vec" key-switch tile shape, "circuit_graph" 0/1 (CUDA-graph replay of circuit levels),
+ * around K1/K2), "ks_tile" / "ks_vec" key-switch tile shape, "ks_fill" CTAs per SM the key switch splits its mask range for (0 = automatic),
+ * "ks_rot" -1 = no staggered starting points, "circuit_graph" 0/1 (CUDA-graph replay of circuit levels),
  * "circuit_lanes" concurrent instance groups per device (read at circuit_create; default 4) */
 int tfhe_b200_set_tuning(tfhe_b200_ctx *ctx, const char *key, int value);
 /* with "timing" on: device time in ms of the last blind-rotation (which = 0) or key-switch (which = 1)

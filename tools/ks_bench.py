@@ -20,9 +20,14 @@ lv1 = torch.randint(-2**31, 2**31 - 1, (B, 1025), dtype=torch.int32, device="cud
 out = torch.empty((B, 701), dtype=torch.int32, device="cuda")
 stream = torch.cuda.ExternalStream(ctx.stream(0))
 ref = None
-for tile, vec in ((8, 1), (8, 2), (4, 2), (4, 1), (16, 1)):
+FILLS = [int(x) for x in os.environ.get("FILLS", "0").split(",")]     # CTAs per SM the i-range split aims for (0 = automatic)
+TILES = [tuple(int(y) for y in x.split("x")) for x in os.environ.get("TILES", "8x1,8x2,4x2,4x1,16x1").split(",")]
+ROTS = [int(x) for x in os.environ.get("ROTS", "0").split(",")]
+for tile, vec, fill, rot in [(t, v, f, r) for (t, v) in TILES for f in FILLS for r in ROTS]:
+    ctx.set_tuning("ks_rot", rot)
     ctx.set_tuning("ks_tile", tile)
     ctx.set_tuning("ks_vec", vec)
+    ctx.set_tuning("ks_fill", fill)
     for _ in range(2):
         ctx.keyswitch_batch_device(0, lv1.data_ptr(), out.data_ptr(), B)
     ctx.sync()
@@ -36,5 +41,5 @@ for tile, vec in ((8, 1), (8, 2), (4, 2), (4, 1), (16, 1)):
     o = out.cpu().numpy()
     if ref is None:
         ref = o.copy()
-    print(f"tile={tile:2d} vec={vec} B={B} K2={ms:.2f} ms  ({B / ms * 1e3:.0f} keyswitch/s)  same_bits={bool((o == ref).all())}", flush=True)
+    print(f"tile={tile:2d} vec={vec} fill={fill:2d} rot={rot} B={B} K2={ms:.2f} ms  ({B / ms * 1e3:.0f} keyswitch/s)  same_bits={bool((o == ref).all())}", flush=True)
 ctx.close()

@@ -60,7 +60,7 @@ struct tfhe_b200_ctx {
     BrTuning tune;
     uint64_t launches = 0;
     bool timing = false;
-    int ks_tile = 0, ks_vec = 0;          // key-switch tuning overrides (0 = automatic)
+    int ks_tile = 0, ks_vec = 0, ks_fill = 0, ks_rot = 0;   // key-switch tuning overrides (0 = automatic)
     size_t max_chunk = (size_t)1 << 18;   // ciphertexts per device per launch
     bool circuit_graph = true;            // replay a circuit's level sequence as one CUDA graph
     int circuit_lanes = 4;                // independent instance groups per device, each on its own stream (set before circuit_create)
@@ -145,6 +145,7 @@ int run_device(tfhe_b200_ctx *c, Device &d, int op, const int32_t *d_ops, const 
     if (d_lv0) {
         if (!c->has_ksk) return fail(c, TFHE_B200_ERR_NO_KEY, "no key-switching key loaded");
         KsArgs K{lv1, d_lv0, d.ksk, (uint32_t)B, c->prm.n, c->prm.basebit, c->prm.iks_t, c->ksk_pitch, kN, c->ks_tile, c->ks_vec};
+        K.fill = c->ks_fill; K.rot = c->ks_rot;
         CU(c, launch_keyswitch(K, d.sm_count, d.stream, &d.launches));
     }
     if (c->timing) {
@@ -578,6 +579,7 @@ int tfhe_b200_keyswitch_batch(tfhe_b200_ctx *c, const uint32_t *lv1, uint32_t *l
             if (int r = ensure(c, d.out, nb * w0 * 4)) return r;
             CU(c, cudaMemcpyAsync(d.lv1.p, lv1 + off * w1, nb * w1 * 4, cudaMemcpyHostToDevice, d.stream));
             KsArgs K{(uint32_t *)d.lv1.p, (uint32_t *)d.out.p, d.ksk, (uint32_t)nb, c->prm.n, c->prm.basebit, c->prm.iks_t, c->ksk_pitch, kN, c->ks_tile, c->ks_vec};
+            K.fill = c->ks_fill; K.rot = c->ks_rot;
             CU(c, launch_keyswitch(K, d.sm_count, d.stream, &c->launches));
             CU(c, cudaMemcpyAsync(lv0 + off * w0, d.out.p, nb * w0 * 4, cudaMemcpyDeviceToHost, d.stream));
             CU(c, cudaStreamSynchronize(d.stream));
@@ -622,6 +624,7 @@ int tfhe_b200_reencrypt_batch(tfhe_b200_ctx *c, const uint32_t *in, uint32_t *ou
             if (int r = ensure(c, d.out, nb * w * 4)) return r;
             CU(c, cudaMemcpyAsync(d.a.p, in + off * w, nb * w * 4, cudaMemcpyHostToDevice, d.stream));
             KsArgs K{(uint32_t *)d.a.p, (uint32_t *)d.out.p, d.reenc, (uint32_t)nb, c->prm.n, c->reenc_basebit, c->reenc_t, c->ksk_pitch, c->prm.n, c->ks_tile, c->ks_vec};
+            K.fill = c->ks_fill; K.rot = c->ks_rot;
             CU(c, launch_keyswitch(K, d.sm_count, d.stream, &c->launches));
             CU(c, cudaMemcpyAsync(out + off * w, d.out.p, nb * w * 4, cudaMemcpyDeviceToHost, d.stream));
             CU(c, cudaStreamSynchronize(d.stream));
@@ -670,6 +673,7 @@ int tfhe_b200_keyswitch_batch_device(tfhe_b200_ctx *c, int dev, const uint32_t *
     Device &d = c->devs[dev];
     CU(c, cudaSetDevice(d.id));
     KsArgs K{d_lv1, d_lv0, d.ksk, (uint32_t)B, c->prm.n, c->prm.basebit, c->prm.iks_t, c->ksk_pitch, kN, c->ks_tile, c->ks_vec};
+    K.fill = c->ks_fill; K.rot = c->ks_rot;
     CU(c, launch_keyswitch(K, d.sm_count, d.stream, &c->launches));
     return 0;
 }
@@ -946,6 +950,8 @@ int tfhe_b200_set_tuning(tfhe_b200_ctx *c, const char *key, int value) {
     else if (!strcmp(key, "timing")) c->timing = value != 0;
     else if (!strcmp(key, "ks_tile")) c->ks_tile = value;
     else if (!strcmp(key, "ks_vec")) c->ks_vec = value;
+    else if (!strcmp(key, "ks_fill")) c->ks_fill = value;
+    else if (!strcmp(key, "ks_rot")) c->ks_rot = value;
     else if (!strcmp(key, "circuit_graph")) c->circuit_graph = value != 0;
     else if (!strcmp(key, "circuit_lanes")) c->circuit_lanes = value;
     else if (!strcmp(key, "max_chunk")) c->max_chunk = value > 0 ? (size_t)value : c->max_chunk;

@@ -57,6 +57,8 @@ struct KsArgs {
     int n, basebit, iks_t, pitch;   // pitch = row length in u32 (multiple of 4)
     int in_dim;                     // mask length of the source samples: N (key switch) or n (proxy re-encryption)
     int tile = 0, vec = 0;          // tuning overrides (0 = automatic): ciphertexts per CTA, uint4 vectors per thread
+    int fill = 0;                   // tuning override: CTAs per SM the i-range split aims for (0 = automatic)
+    int rot = 0;                    // -1: every CTA walks i from the start of its range (default: staggered starting points)
 };
 cudaError_t launch_keyswitch(const KsArgs &a, int sm_count, cudaStream_t s, uint64_t *launches);
 

@@ -66,7 +66,11 @@ __global__ void __launch_bounds__(320) keyswitch_kernel(const KsArgs P, int i_pe
 
     const uint4 *ksk4 = reinterpret_cast<const uint4 *>(P.ksk);
     const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
-    for (int i = i0; i < i1; i++) {
+    // every CTA walks its i range from a different starting point (the subtraction order is free): CTAs that start
+    // together do not pull the same key rows through the same L2 slices at the same time
+    const int span = i1 - i0;
+    int i = i0 + (P.rot >= 0 && span > 0 ? (int)((blockIdx.x * 37u) % (unsigned)span) : 0);
+    for (int k = 0; k < span; k++, i = (i + 1 == i1) ? i0 : i + 1) {
         uint32_t ab[CT];
 #pragma unroll
         for (int c = 0; c < CT; c++) ab[c] = abar[c * i_per_split + (i - i0)];
@@ -184,15 +188,20 @@ __global__ void extract2_kernel(const uint32_t *lv1, uint32_t *out, uint32_t B, 
 cudaError_t launch_keyswitch(const KsArgs &a, int sm_count, cudaStream_t s, uint64_t *launches) {
     if (a.B == 0) return cudaSuccess;
     if (a.pitch > 320 * 4) return cudaErrorInvalidValue;
-    // pick the tile so the grid fills the machine; split the i range for small batches
-    // measured on B200 at B = 65,536 (tools/ks_bench.py): tile 8 = 61 ms, 16 = 84 ms, 4 = 68 ms, 32 = 178 ms:
-    // the kernel is latency-bound, small tiles keep ~7 CTAs per SM resident and the rows hit in L1
-    int ct = (a.B >= (uint32_t)(8 * sm_count)) ? 8 : 4;
+    // Tile and split, measured on B200 (tools/ks_bench.py, profiles/r01_ks_split_sweep.log):
+    //  * tile 8 from 32 ciphertexts up (at B = 65,536: tile 8 = 60 ms, 4 = 70 ms, 16 = 83 ms; at B = 74..2,048 tile 4 re-reads the
+    //    key through L2 once per tile and is 1.5-2x slower than tile 8);
+    //  * the i range is split over blockIdx.y until the grid holds `fill` CTAs per SM, partial results combined with u32
+    //    atomics (order-free): 64 per SM from 1,024 ciphertexts up -- also at B = 65,536, where two splits take 51 ms against 60 ms
+    //    for one (shorter CTAs: 19 instead of 9.2 waves of 6 resident CTAs, and different i ranges in flight at once) -- and 16
+    //    below that (B = 148: 0.18 ms against 0.67 ms with the 2 per SM of the first version).
+    int ct = (a.B >= 32u) ? 8 : 4;
     if (a.tile == 4 || a.tile == 8 || a.tile == 16) ct = a.tile;
     const int tiles = (a.B + ct - 1) / ct;
     int splits = 1;
     // (up to 256 splits: a single ciphertext then walks 4 mask entries per CTA instead of a 288-step dependent chain)
-    while (tiles * splits < 2 * sm_count && splits < 256) splits *= 2;
+    const int fill = a.fill > 0 ? a.fill : (a.B >= 1024u ? 64 : 16);
+    while ((long long)tiles * splits < (long long)fill * sm_count && splits < 256) splits *= 2;
     cudaError_t e;
     if (splits > 1) {
         e = cudaMemsetAsync(a.lv0, 0, (size_t)a.B * (a.n + 1) * sizeof(uint32_t), s);
