@@ -5,11 +5,17 @@
   python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
   python bench.py --impl reference ...                            (host-CPU arm)
 
-Workload (BASELINE.json configs[1]): 65,536 independent AND/XOR gates (half each) at
+Default workload (BASELINE.json configs[1]): 65,536 independent AND/XOR gates (half each) at
 SECURITY_128_BIT per GPU ("weak" scaling: every rank owns its own 65,536-gate shard; keys are
 generated once on rank 0 and broadcast with one NCCL broadcast at key load; there is no collective
 on the hot path).  One step = one pass of the whole path (gate linear part -> blind rotation ->
 sample extract -> key switch) over the batch.
+
+The other BASELINE configs from the same build (the default line is unchanged by these flags):
+  --params {80,110,128}            parameter set of the gate workload (configs[4])
+  --params uint4 [--mode exact|fast]  programmable LUT bootstraps at SECURITY_UINT4, 32,768 per GPU (configs[3]);
+                                   exact mode (the reference's own transform DAG) is the one that equals the oracle there
+  --total N --scaling strong       N units in total, a contiguous shard of N / world per rank (configs[4]: --total 1048576)
 
   value : gates/s with inputs already resident in HBM (device entry points, CUDA events on the
           library's stream, max over ranks).
@@ -37,25 +43,56 @@ sys.path.insert(0, os.path.join(ROOT, "zig-tfhe_b200"))
 
 PARAMS = "128"
 BATCH = 65536
-METRIC = "bootstrapped gates/sec (whole box, 128-bit)"
+LUT_BATCH = 32768
 UNIT = "gates/s"
-# algorithmic work per bootstrap, SURVEY.md section 8d / BASELINE.md section 3 (128-bit set)
-FLOP_PER_BOOTSTRAP = 180_633_600
-BSK_BYTES = 68_812_800
-KSK_BYTES = 103_366_656
 AND, XOR = 2, 3
+LUT_MODULUS = 16
+
+
+def metric_name(pname, mode):
+    if pname.startswith("uint"):
+        return f"LUT bootstraps/sec (whole box, {pname.upper()}, {mode} mode)"
+    return f"bootstrapped gates/sec (whole box, {pname}-bit)"
+
+
+def work_per_bootstrap(p):
+    """algorithmic work per bootstrap, SURVEY.md section 8d: n x ((2L+2) transforms x 26,112 flop + 2L x 2 x 512 complex MACs x 8 flop);
+    key bytes as in SURVEY.md appendix B"""
+    flop = p.n * ((2 * p.L + 2) * 26112 + 2 * p.L * 2 * 512 * 8)
+    bsk = p.n * 2 * p.L * 2 * 1024 * 8
+    ksk = 1024 * p.iks_t * (1 << p.basebit) * (p.n + 1) * 4
+    return flop, bsk, ksk
 
 
 def synth_inputs(params, sk, batch, seed):
+    """gate workload: `batch` AND/XOR gates (half each) on encryptions of uniform random bits.  Above 65,536 the distinct
+    ciphertext pairs are tiled (host-side encryption is numpy; the device work does not depend on the values)."""
     from tfhe_b200 import hostkeys as HK
     rng = np.random.default_rng(seed)
-    a = rng.integers(0, 2, batch).astype(np.uint8)
-    b = rng.integers(0, 2, batch).astype(np.uint8)
+    D = min(batch, 65536)
+    a = rng.integers(0, 2, D).astype(np.uint8)
+    b = rng.integers(0, 2, D).astype(np.uint8)
     ca = HK.encrypt_bools(a, params, sk, rng)
     cb = HK.encrypt_bools(b, params, sk, rng)
+    if batch > D:
+        reps = -(-batch // D)
+        a, b = np.tile(a, reps)[:batch], np.tile(b, reps)[:batch]
+        ca, cb = np.tile(ca, (reps, 1))[:batch], np.tile(cb, (reps, 1))[:batch]
     ops = np.where(np.arange(batch) < batch // 2, AND, XOR).astype(np.int32)
     truth = np.where(ops == AND, a & b, a ^ b).astype(np.uint8)
     return ca, cb, ops, truth
+
+
+def synth_lut_inputs(params, sk, batch, seed):
+    """LUT workload (BASELINE configs[3]): encryptions of uniform messages in [0, 16) (tlwe.encryptLweMessage, src/tlwe.zig:72-90)
+    and the test vector of f(x) = x^2 mod 16 (lut/generator.zig:85-135)"""
+    from tfhe_b200 import hostkeys as HK
+    from tfhe_b200 import lut as LUT
+    rng = np.random.default_rng(seed)
+    msgs = rng.integers(0, LUT_MODULUS, batch)
+    ct = HK.tlwe_encrypt_f64(msgs / (2.0 * LUT_MODULUS), HK.ALPHAS[params.name][0], sk.key_lv0, rng)
+    tv = LUT.Generator(LUT_MODULUS).generate_lookup_table(lambda x: (x * x) % LUT_MODULUS).poly
+    return ct, np.ascontiguousarray(tv, dtype=np.uint32)
 
 
 class ClockSampler:
@@ -100,23 +137,55 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_rate(keys_tuple, ca, cb, ops, seconds_target=12.0):
-    """times the CPU oracle (port of the reference path) with all host threads on a bounded sample"""
+def oracle_for(pname, sk, ck):
     sys.path.insert(0, ROOT)
     from oracle import oracle as O
-    sk, ck = keys_tuple
-    orc = O.Oracle(PARAMS)
+    orc = O.Oracle(pname)
     keys = O.Keys(sk.key_lv0, sk.key_lv1, ck.bootstrapping_key, ck.key_switching_key, ck.decomposition_offset, ck.blind_rotate_testvec)
+    return O, orc, keys
+
+
+def cpu_run(orc, keys, work, lo, hi, nthreads):
+    """one pass of the CPU oracle (port of the reference path) over items [lo, hi) of the workload"""
+    if work["kind"] == "lut":
+        return orc.bootstrap_batch(work["ct"][lo:hi], keys, work["tv"], nthreads=nthreads)
+    return orc.gate_batch(work["ops"][lo:hi], work["ca"][lo:hi], work["cb"][lo:hi], keys, nthreads=nthreads)
+
+
+def cpu_reference_rate(pname, keys_tuple, work, seconds_target=12.0):
+    """times the CPU oracle with all host threads on a bounded sample, and one thread on a few items (ms per bootstrap,
+    the figure the reference's CHANGELOG quotes)"""
+    O, orc, keys = oracle_for(pname, *keys_tuple)
     cores = O.hardware_threads()
-    probe = min(len(ca), 2 * cores)
+    n_items = work["n"]
+    probe = min(n_items, 2 * cores)
     t0 = time.perf_counter()
-    orc.gate_batch(ops[:probe], ca[:probe], cb[:probe], keys, nthreads=cores)
-    per_round = (time.perf_counter() - t0) / 2.0          # seconds for `cores` gates
-    sample = int(min(len(ca), max(4 * cores, cores * max(1, int(seconds_target / max(per_round, 1e-3))))))
+    cpu_run(orc, keys, work, 0, probe, cores)
+    per_round = (time.perf_counter() - t0) / 2.0          # seconds for `cores` items
+    sample = int(min(n_items, max(4 * cores, cores * max(1, int(seconds_target / max(per_round, 1e-3))))))
     t0 = time.perf_counter()
-    out = orc.gate_batch(ops[:sample], ca[:sample], cb[:sample], keys, nthreads=cores)
+    out = cpu_run(orc, keys, work, 0, sample, cores)
     dt = time.perf_counter() - t0
-    return sample / dt, cores, sample, out
+    k1 = min(n_items, 8)
+    t0 = time.perf_counter()
+    cpu_run(orc, keys, work, 0, k1, 1)
+    single_ms = (time.perf_counter() - t0) * 1e3 / k1
+    return sample / dt, cores, sample, out, single_ms
+
+
+def make_work(pname, params, sk, batch, seed):
+    if pname.startswith("uint"):
+        ct, tv = synth_lut_inputs(params, sk, batch, seed)
+        return {"kind": "lut", "n": batch, "ct": ct, "tv": tv}
+    ca, cb, ops, truth = synth_inputs(params, sk, batch, seed)
+    return {"kind": "gates", "n": batch, "ca": ca, "cb": cb, "ops": ops, "truth": truth}
+
+
+def workload_text(pname, B, mode, scaling, total, world):
+    per = f"{B} per GPU" if scaling == "weak" else f"{total} in total, a contiguous shard of {B} per GPU"
+    if pname.startswith("uint"):
+        return f"programmable LUT bootstraps (x^2 mod 16, shared test vector) at SECURITY_{pname.upper()}, {mode} mode, {per}"
+    return f"independent AND/XOR gates (half/half) at SECURITY_{pname}_BIT, {per}, seeded keys and ciphertexts"
 
 
 def run_reference(args):
@@ -126,41 +195,46 @@ def run_reference(args):
         return
     import tfhe_b200
     from tfhe_b200 import hostkeys as HK
-    params = tfhe_b200.PARAM_SETS[PARAMS]
+    pname = args.params
+    params = tfhe_b200.PARAM_SETS[pname]
     sk, ck = HK.gen_cloud_key(params, seed=1)
     sample_max = 4096
-    ca, cb, ops, truth = synth_inputs(params, sk, sample_max, seed=42)
+    work = make_work(pname, params, sk, sample_max, seed=42)
     rates = []
-    sys.path.insert(0, ROOT)
-    from oracle import oracle as O
-    orc = O.Oracle(PARAMS)
-    keys = O.Keys(sk.key_lv0, sk.key_lv1, ck.bootstrapping_key, ck.key_switching_key, ck.decomposition_offset, ck.blind_rotate_testvec)
+    O, orc, keys = oracle_for(pname, sk, ck)
     cores = O.hardware_threads()
-    sample = int(min(sample_max, max(2 * cores, 16 * cores)))
     total = args.warmup + args.steps
     budget = 150.0
     t_probe = time.perf_counter()
-    orc.gate_batch(ops[:cores], ca[:cores], cb[:cores], keys, nthreads=cores)
+    cpu_run(orc, keys, work, 0, cores, cores)
     per_round = time.perf_counter() - t_probe
     rounds = max(1, min(16, int(budget / total / max(per_round, 1e-3))))
     sample = min(sample_max, rounds * cores)
     ok = True
     for step in range(total):
         t0 = time.perf_counter()
-        out = orc.gate_batch(ops[:sample], ca[:sample], cb[:sample], keys, nthreads=cores)
+        out = cpu_run(orc, keys, work, 0, sample, cores)
         dt = time.perf_counter() - t0
         if step >= args.warmup:
             rates.append(sample / dt)
-        ok = ok and bool((HK.decrypt_bools(out, sk) == truth[:sample]).all())
+        if work["kind"] == "gates":
+            ok = ok and bool((HK.decrypt_bools(out, sk) == work["truth"][:sample]).all())
+    t0 = time.perf_counter()
+    cpu_run(orc, keys, work, 0, 4, 1)
+    single_ms = (time.perf_counter() - t0) * 1e3 / 4
     value = float(np.mean(rates))
+    B = args.batch or (LUT_BATCH if work["kind"] == "lut" else BATCH)
+    unit = UNIT if work["kind"] == "gates" else "bootstraps/s"
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * sample / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": {"workload": f"AND/XOR gates at SECURITY_128_BIT, bounded sample of {sample} gates per step (of {BATCH})",
-                                        "params": PARAMS, "batch_per_step": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} gates per step, {args.steps} timed steps, std::thread static partition over {cores} threads"},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": metric_name(pname, args.mode), "value": value, "unit": unit,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sample / value, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": workload_text(pname, B, args.mode, args.scaling, args.total, args.gpus) +
+                                        f"; bounded sample of {sample} per step on the host CPU", "params": pname, "batch_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port",
+                         "sample": f"{sample} items per step, {args.steps} timed steps, std::thread static partition over {cores} threads",
+                         "single_thread_ms_per_bootstrap": single_ms},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "outputs_correct": ok, "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -172,11 +246,18 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH, help="gates per GPU per step (default: the BASELINE configuration)")
+    ap.add_argument("--params", default=PARAMS, choices=["80", "110", "128", "uint4"], help="parameter set (uint4: LUT bootstrap workload)")
+    ap.add_argument("--mode", default=None, choices=["fast", "exact"], help="transform mode (default: fast; exact for uint4)")
+    ap.add_argument("--batch", type=int, default=0, help="units per GPU per step (default: 65,536 gates / 32,768 LUT bootstraps)")
+    ap.add_argument("--total", type=int, default=0, help="units per step over all GPUs (with --scaling strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--kct", type=int, default=0)
     ap.add_argument("--no-tma", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pageable", action="store_true", help="e2e leg from pageable host memory (what a Zig caller's page_allocator gives)")
     args = ap.parse_args()
+    if args.mode is None:
+        args.mode = "exact" if args.params.startswith("uint") else "fast"
     if args.impl == "reference":
         return run_reference(args)
     if args.warmup < 3:
@@ -195,12 +276,21 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    params = tfhe_b200.PARAM_SETS[PARAMS]
-    B = args.batch
+    pname = args.params
+    params = tfhe_b200.PARAM_SETS[pname]
+    is_lut = pname.startswith("uint")
+    from tfhe_b200 import dist as D
+    if args.scaling == "strong":
+        total = args.total or (1 << 20)
+        lo, hi = D.shard_range(total, rank, world)
+        B = hi - lo
+    else:
+        B = args.batch or (LUT_BATCH if is_lut else BATCH)
+        total = B * world
     w = params.n + 1
+    FLOP_PER_BOOTSTRAP, BSK_BYTES, KSK_BYTES = work_per_bootstrap(params)
 
     # ---- keys: generated on rank 0, one NCCL broadcast, re-laid-out on device by the library
-    from tfhe_b200 import dist as D
     ctx = tfhe_b200.Context(params, devices=[local_rank])
     sk = ck = None
     if rank == 0:
@@ -217,14 +307,23 @@ def main():
         torch.cuda.empty_cache()
     else:
         ctx.load_cloud_key(ck)
+    if args.mode == "exact":
+        ctx.set_mode(tfhe_b200.MODE_EXACT)
 
     # ---- synthetic inputs (this rank's shard), pinned on the host and resident on the device
-    ca, cb, ops, truth = synth_inputs(params, sk, B, seed=42 + rank)
-    h_a = torch.from_numpy(ca.view(np.int32)).pin_memory()
-    h_b = torch.from_numpy(cb.view(np.int32)).pin_memory()
-    h_ops = torch.from_numpy(ops).pin_memory()
-    h_out = torch.empty((B, w), dtype=torch.int32).pin_memory()
-    d_a, d_b, d_ops = h_a.to(dev), h_b.to(dev), h_ops.to(dev)
+    work = make_work(pname, params, sk, B, seed=42 + rank)
+    pin = (lambda t: t) if args.pageable else (lambda t: t.pin_memory())
+    if is_lut:
+        h_a = pin(torch.from_numpy(work["ct"].view(np.int32)))
+        h_tv = pin(torch.from_numpy(work["tv"].view(np.int32)))
+        d_a, d_tv = h_a.to(dev), h_tv.to(dev)
+        h_b = h_ops = d_b = d_ops = None
+    else:
+        h_a = pin(torch.from_numpy(work["ca"].view(np.int32)))
+        h_b = pin(torch.from_numpy(work["cb"].view(np.int32)))
+        h_ops = pin(torch.from_numpy(work["ops"]))
+        d_a, d_b, d_ops = h_a.to(dev), h_b.to(dev), h_ops.to(dev)
+    h_out = pin(torch.empty((B, w), dtype=torch.int32))
     d_out = torch.empty((B, w), dtype=torch.int32, device=dev)
     torch.cuda.synchronize()
     if args.kct:
@@ -240,8 +339,11 @@ def main():
         torch.cuda.synchronize()
         ctx.sync()
 
-    def step_device():
-        ctx.gate_batch_device(0, 0, d_ops.data_ptr(), d_a.data_ptr(), d_b.data_ptr(), d_out.data_ptr(), B)
+    def step_device(n=B):
+        if is_lut:
+            ctx.bootstrap_batch_device(0, d_a.data_ptr(), d_out.data_ptr(), n, d_tv.data_ptr(), False)
+        else:
+            ctx.gate_batch_device(0, 0, d_ops.data_ptr(), d_a.data_ptr(), d_b.data_ptr(), d_out.data_ptr(), n)
 
     fp64_peak = ctx.measure_fp64_tflops(0)
 
@@ -269,28 +371,36 @@ def main():
         ctx.sync()
         k1_ms.append(ctx.last_kernel_ms(0, 0)); k2_ms.append(ctx.last_kernel_ms(0, 1))
     out_dev = d_out.cpu().numpy().view(np.uint32)
-    ok_dev = bool((HK.decrypt_bools(out_dev, sk) == truth).all())
+    ok_dev = True if is_lut else bool((HK.decrypt_bools(out_dev, sk) == work["truth"]).all())
 
     # ---- end to end through the host-buffer C ABI (H2D + kernels + D2H per step); per-kernel event timing off: this is
     # the call exactly as a user makes it
     ctx.set_tuning("timing", 0)
-    a_np, b_np, ops_np, out_np = h_a.numpy().view(np.uint32), h_b.numpy().view(np.uint32), h_ops.numpy(), h_out.numpy().view(np.uint32)
-    ctx.gate_batch(ops_np, a_np, b_np, out=out_np)
+    out_np = h_out.numpy().view(np.uint32)
+    if is_lut:
+        a_np, tv_np = h_a.numpy().view(np.uint32), h_tv.numpy().view(np.uint32)
+        step_host = lambda: ctx.bootstrap_batch(a_np, tv_np, out=out_np)
+        h2d, d2h = B * w * 4 + 2 * 1024 * 4, B * w * 4
+    else:
+        a_np, b_np, ops_np = h_a.numpy().view(np.uint32), h_b.numpy().view(np.uint32), h_ops.numpy()
+        step_host = lambda: ctx.gate_batch(ops_np, a_np, b_np, out=out_np)
+        h2d, d2h = 2 * B * w * 4 + B * 4, B * w * 4
+    step_host()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ctx.gate_batch(ops_np, a_np, b_np, out=out_np)
+        step_host()
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
-    ok_e2e = bool((HK.decrypt_bools(out_np, sk) == truth).all()) and bool((out_np == out_dev).all())
+    ok_e2e = bool((out_np == out_dev).all()) and (is_lut or bool((HK.decrypt_bools(out_np, sk) == work["truth"]).all()))
 
-    # ---- p50 latency of a single bootstrapped gate (B = 1, device resident)
+    # ---- p50 latency of a single bootstrap (B = 1, device resident)
     lat = []
     for _ in range(15):
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record(stream)
-        ctx.gate_batch_device(0, 0, d_ops.data_ptr(), d_a.data_ptr(), d_b.data_ptr(), d_out.data_ptr(), 1)
+        step_device(1)
         s1.record(stream)
         ctx.sync()
         lat.append(s0.elapsed_time(s1))
@@ -306,9 +416,9 @@ def main():
         dist.all_reduce(flags, op=dist.ReduceOp.MIN)
 
     if rank == 0:
-        total_gates = B * world * args.steps
-        value = total_gates / (dev_ms_max * 1e-3)
-        e2e = total_gates / (e2e_ms_max * 1e-3)
+        total_units = total * args.steps
+        value = total_units / (dev_ms_max * 1e-3)
+        e2e = total_units / (e2e_ms_max * 1e-3)
         k1 = float(np.mean(k1_ms)); k2 = float(np.mean(k2_ms))
         achieved_tflops = FLOP_PER_BOOTSTRAP * B / (k1 * 1e-3) / 1e12
         peaks = {}
@@ -317,44 +427,56 @@ def main():
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        sm_mhz = clocks.get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+        arith_peak = 148 * 64 * 2 * sm_mhz * 1e6 / 1e12      # 64 FP64 FMA lanes per SM per clock
         kct = args.kct or 4
         waves = -(-B // (148 * kct))
-        io_bytes = B * (2 * w * 4 + 4 + 4100)           # two operands + opcode in, one lv1 sample out
-        traffic = None                                  # dram bytes per launch of K1 from the committed ncu capture
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_k1_traffic.json")))
-            if B == BATCH and not args.kct:
-                traffic = tr["dram_bytes_total"]
-        except Exception:
-            pass
+        io_bytes = B * ((1 if is_lut else 2) * w * 4 + 4 + 4100)      # operands + opcode in, one lv1 sample out
+        traffic, traffic_src = None, None                  # dram bytes per launch of K1 from the committed ncu capture
+        for name in ("r02_k1_traffic.json", "r01_k1_traffic.json"):
+            try:
+                tr = json.load(open(os.path.join(ROOT, "profiles", name)))
+                if B == BATCH and pname == PARAMS and args.mode == "fast" and not args.kct:
+                    traffic, traffic_src = tr["dram_bytes_total"], name
+                break
+            except Exception:
+                continue
         roofline = {
-            "kernel": "blind_rotate_kernel", "bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+            "kernel": "blind_rotate_exact_kernel" if args.mode == "exact" else "blind_rotate_kernel", "bound": "fp64",
+            "achieved": achieved_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
             "frac": achieved_tflops / fp64_peak if fp64_peak > 0 else None, "traffic": traffic,
-            "traffic_source": "profiles/r01_k1_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, one launch of this workload)",
+            "traffic_source": f"profiles/{traffic_src} (ncu dram__bytes_read.sum + dram__bytes_write.sum, one launch of this workload; a committed "
+                              "capture, not measured in this run)" if traffic_src else None,
             "peak_source": "measured live by tfhe_b200_measure_fp64_tflops (DFMA microbenchmark); MEASURED_PEAKS.json has no FP64 figure",
+            "peak_arithmetic": arith_peak, "frac_of_arithmetic_peak": achieved_tflops / arith_peak,
+            "peak_arithmetic_source": f"148 SMs x 64 FP64 FMA lanes x 2 flop x {sm_mhz:.0f} MHz (median SM clock under load in this run)",
             "algorithmic_flop_per_bootstrap": FLOP_PER_BOOTSTRAP, "kernel_ms": k1, "kernel_share_of_step": k1 / (k1 + k2),
             "hbm": {"algorithmic_bytes": BSK_BYTES * waves + io_bytes, "achieved_gbs": (BSK_BYTES * waves + io_bytes) / (k1 * 1e-3) / 1e9,
                     "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                     "note": f"north_star's amortised-key term: each of the {waves} lock-step CTA waves ({148 * kct} bootstraps) streams the "
-                            "68.8 MB key from HBM once and shares it through L2; far from the HBM bound (the kernel is FP64/shared-memory bound)"},
-            "keyswitch": {"kernel_ms": k2, "algorithmic_bytes": KSK_BYTES * 3 // 4 + B * (4100 + w * 4),
-                          "achieved_gbs": (KSK_BYTES * 3 // 4 + B * (4100 + w * 4)) / (k2 * 1e-3) / 1e9},
+                            f"{BSK_BYTES / 1e6:.1f} MB key from HBM once and shares it through L2; far from the HBM bound (the kernel is FP64/shared-memory bound)"},
+            "keyswitch": {"kernel_ms": k2, "algorithmic_bytes": KSK_BYTES * ((1 << params.basebit) - 1) // (1 << params.basebit) + B * (4100 + w * 4),
+                          "achieved_gbs": (KSK_BYTES * ((1 << params.basebit) - 1) // (1 << params.basebit) + B * (4100 + w * 4)) / (k2 * 1e-3) / 1e9},
         }
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": f"{B} independent AND/XOR gates (half/half) at SECURITY_128_BIT per GPU, seeded keys and ciphertexts",
-                       "params": PARAMS, "batch_per_gpu": B, "parallelism": f"batch-sharded x{world}, keys replicated (one NCCL broadcast at load)",
-                       "l2": "inputs (367 MB per step) larger than L2; keys (172 MB) larger than L2"},
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(2 * B * w * 4 + B * 4), "d2h_bytes_per_step": int(B * w * 4)},
+            "metric": metric_name(pname, args.mode), "value": value, "unit": "bootstraps/s" if is_lut else UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_text(pname, B, args.mode, args.scaling, total, world),
+                       "params": pname, "mode": args.mode, "batch_per_gpu": B, "total_per_step": total,
+                       "parallelism": f"batch-sharded x{world}, keys replicated (one NCCL broadcast at load)",
+                       "host_memory": "pageable" if args.pageable else "pinned",
+                       "l2": f"inputs ({h2d / 1e6:.0f} MB per step) larger than L2; keys ({(BSK_BYTES + KSK_BYTES * 3 // 4) / 1e6:.0f} MB) larger than L2"},
+            "e2e": {"value": e2e, "unit": "bootstraps/s" if is_lut else UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "latency_ms_p50_single_gate": lat_p50,
             "roofline": roofline, "clocks": clocks, "outputs_correct": bool(flags[0].item() and flags[1].item()),
         }
         if world == 1 and not args.no_cpu_baseline:
-            rate, cores, sample, out_cpu = cpu_reference_rate((sk, ck), ca, cb, ops)
-            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"first {sample} gates of the same batch, oracle C++ port, {cores} std::threads",
+            rate, cores, sample, out_cpu, single_ms = cpu_reference_rate(pname, (sk, ck), work)
+            line["cpu_baseline"] = {"value": rate, "unit": line["unit"], "cores": cores, "kind": "port",
+                                    "sample": f"first {sample} items of the same batch, oracle C++ port, {cores} std::threads",
+                                    "single_thread_ms_per_bootstrap": single_ms,
+                                    "published_single_thread_ms_per_gate": 36.73,
                                     "matches_gpu_bit_exact": bool((out_cpu == out_dev[:sample]).all())}
         print(json.dumps(line), flush=True)
     ctx.close()

@@ -104,7 +104,11 @@ int tfhe_b200_load_key_device(tfhe_b200_ctx *ctx, int dev, const double *d_bsk, 
  * the secret key the caller holds (key_lv0: uint32_t[n], key_lv1: uint32_t[N], entries 0/1 as in key.SecretKey,
  * src/key.zig:23-58).  ksk_alpha / bsk_alpha = params.KSK_ALPHA / BSK_ALPHA (src/params.zig:419-422).
  * Randomness: Philox4x32-10 keyed by `seed` (the reference's own seeding is a clock, src/utils.zig:16-22), so every
- * device of the context generates the identical key and a key is reproducible from its seed.  The keys are written
+ * device of the context generates the identical key and a key is reproducible from its seed.
+ * SECURITY: every mask and noise word of the cloud key is a function of `seed`, so whoever learns the seed can strip the
+ * noise and solve for both secret keys -- the seed is secret-key-equivalent and caps the key's security at 64 bits.  Draw it
+ * from the same entropy source as the secret key, never reuse or publish it; fixed seeds are for tests and benchmarks only.
+ * (The reference's clock-seeded xoshiro is not cryptographic either; production keys want a >= 128-bit seed.)  The keys are written
  * straight into the device layouts; bsk_out / ksk_out (either may be NULL) receive the reference layouts described
  * at the top of this file, e.g. to hand the same CloudKey to the CPU implementation or to serialise it. */
 int tfhe_b200_keygen(tfhe_b200_ctx *ctx, const uint32_t *key_lv0, const uint32_t *key_lv1, uint64_t seed, double ksk_alpha,

@@ -264,3 +264,42 @@ def test_mux_naive_circuit_matches_the_reference_composition():
         circ.close()
     finally:
         ctx.close()
+
+
+@pytest.mark.gpu
+def test_circuit_graph_is_recaptured_after_rekey_and_mode_switch():
+    """the captured level graph bakes in key pointers, mode and tuning.  Same circuit, same instance
+    count: run, load another cloud key, run again (oracle under the NEW key), then FAST -> EXACT -> FAST."""
+    import tfhe_b200
+    from tfhe_b200 import circuits
+    orc = O.Oracle("128"); k1 = keys_for("128"); k2 = keys_for("128", seed=2)
+    ctx = tfhe_b200.Context("128", devices=[0])
+    try:
+        gates, n_in, outs = circuits.mux_naive_netlist()
+        rows = np.array([[a, b, c] for a in (0, 1) for b in (0, 1) for c in (0, 1)], np.uint8)
+        want = np.where(rows[:, 0] == 1, rows[:, 1], rows[:, 2])
+
+        def oracle_mux(k, ca, cb, cc):
+            return orc.gate_batch(O.OR, orc.gate_batch(O.AND, ca, cb, k), orc.gate_batch(O.AND, np.stack([orc.gate_not(x) for x in ca]), cc, k), k)
+
+        ctx.load_key(k1.bsk, k1.ksk, k1.offset)
+        circ = tfhe_b200.Circuit(ctx, gates, n_in, outs)
+        in1 = [orc.encrypt_bools(rows[:, j], k1, 41 + j) for j in range(3)]
+        out1 = circ.run(np.stack(in1))[0]
+        assert (out1 == oracle_mux(k1, *in1)).all()
+        ctx.load_key(k2.bsk, k2.ksk, k2.offset)          # frees and reallocates every key buffer
+        in2 = [orc.encrypt_bools(rows[:, j], k2, 51 + j) for j in range(3)]
+        out2 = circ.run(np.stack(in2))[0]
+        assert (orc.decrypt_bools(out2, k2) == want).all()
+        assert (out2 == oracle_mux(k2, *in2)).all()
+        launches = ctx.launch_count()
+        ctx.set_mode(tfhe_b200.MODE_EXACT)               # the exact kernel must actually run: different kernel, same bits here
+        out3 = circ.run(np.stack(in2))[0]
+        assert (out3 == out2).all() and ctx.launch_count() > launches
+        ctx.set_mode(tfhe_b200.MODE_FAST)
+        ctx.set_tuning("kct", 2)
+        assert (circ.run(np.stack(in2))[0] == out2).all()
+        ctx.set_tuning("kct", 0)
+        circ.close()
+    finally:
+        ctx.close()

@@ -130,6 +130,23 @@ def test_integer_oracle_agrees_bit_for_bit(orc128, keys128):
         assert margin < 0.25
 
 
+def test_integer_oracle_follows_a_whole_blind_rotation(orc128, keys128):
+    """all n rows of one bootstrap: the FP64 oracle's accumulator after every CMUX step equals
+    acc + (exact integer negacyclic convolution of the digits of X^a_i acc - acc with row i of the key), mod 2^32 --
+    i.e. the reference's f64 transform path never rounds away from the integer result on this trajectory"""
+    ct = orc128.encrypt_bools(np.array([1], np.uint8), keys128, seed=3)[0]
+    out, trace, margin = orc128.blind_rotate(ct, keys128, trace=True, with_margin=True)
+    assert margin < 0.25
+    btil = 2 * N - ((int(ct[-1]) + (1 << 20)) >> 21)                          # trgsw.zig:297
+    acc = np.stack([O.poly_mul_with_xk(keys128.testvec[h], btil) for h in range(2)])
+    for i in range(orc128.n):
+        at = (int(ct[i]) + (1 << 20)) >> 21                                     # trgsw.zig:312
+        rot = np.stack([O.poly_mul_with_xk(acc[h], at) for h in range(2)])
+        acc = acc + orc128.external_product_int(keys128.bsk[i], rot - acc, keys128.offset)   # cmux, trgsw.zig:260-284
+        assert (acc == trace[i]).all(), f"row {i}"
+    assert (acc == out).all()
+
+
 def test_blind_rotate_and_key_switch_decrypt(orc128, keys128):
     """trgsw.zig:694 "trgsw blind rotate" (we demand 100 %, the reference only 60 %), :729 "identity key switching" """
     bits = np.array([0, 1, 1, 0, 1], np.uint8)

@@ -42,6 +42,7 @@ struct Device {
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // K1 start, K1 end / K2 start, K2 end (timing mode)
     bool ev_valid = false;
     uint64_t launches = 0;             // kernels launched on this device by its host thread (summed by tfhe_b200_launch_count)
+    bool has_key = false, has_ksk = false;   // this device holds a bootstrapping / key-switching key
 };
 
 }  // namespace
@@ -64,6 +65,9 @@ struct tfhe_b200_ctx {
     size_t max_chunk = (size_t)1 << 18;   // ciphertexts per device per launch
     bool circuit_graph = true;            // replay a circuit's level sequence as one CUDA graph
     int circuit_lanes = 4;                // independent instance groups per device, each on its own stream (set before circuit_create)
+    // Bumped by everything a captured circuit graph bakes into its kernel nodes: key buffers (load_key*, keygen), mode,
+    // margin tracking, tuning.  A circuit re-captures when its graph was recorded under another epoch.
+    uint64_t config_epoch = 1;
 };
 
 namespace {
@@ -79,6 +83,15 @@ int fail(tfhe_b200_ctx *c, int code, const char *fmt, ...) {
         c->err = buf;
     }
     return code;
+}
+
+ // a context has a key only when every one of its devices does (tfhe_b200_load_key_device loads one device at a time)
+void refresh_key_flags(tfhe_b200_ctx *c) {
+    bool k = !c->devs.empty(), s = !c->devs.empty();
+    for (const Device &d : c->devs) { k = k && d.has_key; s = s && d.has_ksk; }
+    c->has_key = k;
+    c->has_ksk = s;
+    c->config_epoch++;
 }
 
 #define CU(c, expr)                                                                                       \
@@ -238,44 +251,58 @@ int run_host(tfhe_b200_ctx *c, int op, const int32_t *ops, const uint32_t *a, co
     return 0;
 }
 
+// device allocation released on scope exit unless handed over (error paths of the key upload)
+struct DevTmp {
+    void *p = nullptr;
+    ~DevTmp() { if (p) cudaFree(p); }
+    void *release() { void *q = p; p = nullptr; return q; }
+};
+
 int upload_key_device(tfhe_b200_ctx *c, Device &d, const double *src_bsk, bool bsk_on_device, const uint32_t *src_ksk,
                       bool ksk_on_device, size_t ksk_stride_u32) {
     const tfhe_b200_params &p = c->prm;
     CU(c, cudaSetDevice(d.id));
+    // the key already on the device stays usable until the new one is completely in place
     const size_t bsk_doubles = (size_t)p.n * 2 * p.L * 2 * kN;
     const double *d_ref = src_bsk;
-    double *staging = nullptr;
+    DevTmp staging, fast;
     if (!bsk_on_device) {
-        CU(c, cudaMalloc(&staging, bsk_doubles * 8));
-        CU(c, cudaMemcpyAsync(staging, src_bsk, bsk_doubles * 8, cudaMemcpyHostToDevice, d.stream));
-        d_ref = staging;
+        CU(c, cudaMalloc(&staging.p, bsk_doubles * 8));
+        CU(c, cudaMemcpyAsync(staging.p, src_bsk, bsk_doubles * 8, cudaMemcpyHostToDevice, d.stream));
+        d_ref = (const double *)staging.p;
     }
-    if (d.bsk) CU(c, cudaFree(d.bsk));
-    CU(c, cudaMalloc(&d.bsk, bsk_doubles * 8));
-    CU(c, launch_permute_bsk(d_ref, d.bsk, p.n, p.L, d.stream, &c->launches));
-    if (!staging) {   // caller's device buffer: keep our own copy of the reference layout for exact mode
-        CU(c, cudaMalloc(&staging, bsk_doubles * 8));
-        CU(c, cudaMemcpyAsync(staging, src_bsk, bsk_doubles * 8, cudaMemcpyDeviceToDevice, d.stream));
+    CU(c, cudaMalloc(&fast.p, bsk_doubles * 8));
+    CU(c, launch_permute_bsk(d_ref, (cplx *)fast.p, p.n, p.L, d.stream, &c->launches));
+    if (!staging.p) {   // caller's device buffer: keep our own copy of the reference layout for exact mode
+        CU(c, cudaMalloc(&staging.p, bsk_doubles * 8));
+        CU(c, cudaMemcpyAsync(staging.p, src_bsk, bsk_doubles * 8, cudaMemcpyDeviceToDevice, d.stream));
     }
     CU(c, cudaStreamSynchronize(d.stream));
+    if (d.bsk) CU(c, cudaFree(d.bsk));
+    d.bsk = (cplx *)fast.release();
     if (d.bsk_ref) CU(c, cudaFree(d.bsk_ref));
-    d.bsk_ref = staging;
+    d.bsk_ref = (double *)staging.release();
+    d.has_key = true;
 
-    if (d.ksk) { CU(c, cudaFree(d.ksk)); d.ksk = nullptr; }
-    if (src_ksk) {
+    if (!src_ksk) {
+        d.has_ksk = false;
+        if (d.ksk) { CU(c, cudaFree(d.ksk)); d.ksk = nullptr; }
+    } else {
         const int base = 1 << p.basebit;
         const size_t rows = (size_t)kN * p.iks_t * base;
         const uint32_t *d_refk = src_ksk;
-        uint32_t *stg = nullptr;
+        DevTmp stg, packed;
         if (!ksk_on_device) {
-            CU(c, cudaMalloc(&stg, rows * ksk_stride_u32 * 4));
-            CU(c, cudaMemcpyAsync(stg, src_ksk, rows * ksk_stride_u32 * 4, cudaMemcpyHostToDevice, d.stream));
-            d_refk = stg;
+            CU(c, cudaMalloc(&stg.p, rows * ksk_stride_u32 * 4));
+            CU(c, cudaMemcpyAsync(stg.p, src_ksk, rows * ksk_stride_u32 * 4, cudaMemcpyHostToDevice, d.stream));
+            d_refk = (const uint32_t *)stg.p;
         }
-        CU(c, cudaMalloc(&d.ksk, (size_t)kN * p.iks_t * (base - 1) * c->ksk_pitch * 4));
-        CU(c, launch_repack_ksk(d_refk, ksk_stride_u32, d.ksk, p.n, p.basebit, p.iks_t, c->ksk_pitch, kN, d.stream, &c->launches));
+        CU(c, cudaMalloc(&packed.p, (size_t)kN * p.iks_t * (base - 1) * c->ksk_pitch * 4));
+        CU(c, launch_repack_ksk(d_refk, ksk_stride_u32, (uint32_t *)packed.p, p.n, p.basebit, p.iks_t, c->ksk_pitch, kN, d.stream, &c->launches));
         CU(c, cudaStreamSynchronize(d.stream));
-        if (stg) CU(c, cudaFree(stg));
+        if (d.ksk) CU(c, cudaFree(d.ksk));
+        d.ksk = (uint32_t *)packed.release();
+        d.has_ksk = true;
     }
     return 0;
 }
@@ -305,6 +332,7 @@ struct tfhe_b200_circuit {
         Buf wires, lv1, neg;
         cudaGraphExec_t graph = nullptr;
         size_t graph_inst = 0;
+        uint64_t graph_epoch = 0;        // ctx->config_epoch at capture time
         uint64_t graph_launches = 0;
         bool graph_failed = false;
     };
@@ -333,7 +361,7 @@ int circuit_levels(tfhe_b200_ctx *c, tfhe_b200_circuit *q, Device &dev, tfhe_b20
 // enqueue every level of the circuit for `inst` instances whose input wires are already in pd.wires
 int circuit_enqueue(tfhe_b200_ctx *c, tfhe_b200_circuit *q, Device &d, tfhe_b200_circuit::PerDev &pd, size_t inst) {
     if (!c->circuit_graph || c->timing || pd.graph_failed) return circuit_levels(c, q, d, pd, inst);
-    if (!pd.graph || pd.graph_inst != inst) {
+    if (!pd.graph || pd.graph_inst != inst || pd.graph_epoch != c->config_epoch) {
         if (pd.graph) { cudaGraphExecDestroy(pd.graph); pd.graph = nullptr; }
         const uint64_t before = d.launches;
         cudaGraph_t g = nullptr;
@@ -351,6 +379,7 @@ int circuit_enqueue(tfhe_b200_ctx *c, tfhe_b200_circuit *q, Device &d, tfhe_b200
             return circuit_levels(c, q, d, pd, inst);
         }
         pd.graph_inst = inst;
+        pd.graph_epoch = c->config_epoch;
     }
     CU(c, cudaGraphLaunch(pd.graph, pd.stream));
     d.launches += pd.graph_launches;
@@ -367,9 +396,7 @@ int tfhe_b200_create(const tfhe_b200_params *params, const int *device_ids, int 
     if (!params || !out || n_dev < 1) return TFHE_B200_ERR_INVALID;
     *out = nullptr;
     const tfhe_b200_params &p = *params;
-    if (p.N != kN || p.n < 1 || p.n > 4096 || p.L < 1 || p.L > 4 || p.bgbit < 1 || p.L * p.bgbit > 32 || p.basebit < 1 ||
-        p.basebit > 8 || p.iks_t < 1 || 1 + p.basebit * p.iks_t > 32)
-        return TFHE_B200_ERR_INVALID;
+    if (!tfhe_b200_keyfile::params_supported(p)) return TFHE_B200_ERR_INVALID;
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count < 1) return TFHE_B200_ERR_NO_DEVICE;
     auto *c = new tfhe_b200_ctx();
@@ -433,10 +460,12 @@ int tfhe_b200_load_key(tfhe_b200_ctx *c, const double *bsk, const uint32_t *ksk,
         stride = ksk_row_stride_bytes / 4;
     }
     for (Device &d : c->devs)
-        if (int r = upload_key_device(c, d, bsk, false, ksk, false, stride)) return r;
+        if (int r = upload_key_device(c, d, bsk, false, ksk, false, stride)) {
+            refresh_key_flags(c);
+            return r;
+        }
     c->offset = offset;
-    c->has_key = true;
-    c->has_ksk = ksk != nullptr;
+    refresh_key_flags(c);
     return 0;
 }
 
@@ -458,11 +487,10 @@ int tfhe_b200_load_key_file(tfhe_b200_ctx *c, const char *path) {
 
 int tfhe_b200_load_key_device(tfhe_b200_ctx *c, int dev, const double *d_bsk, const uint32_t *d_ksk, uint32_t offset) {
     if (!c || !d_bsk || dev < 0 || dev >= (int)c->devs.size()) return fail(c, TFHE_B200_ERR_INVALID, "bad argument");
-    if (int r = upload_key_device(c, c->devs[dev], d_bsk, true, d_ksk, true, (size_t)c->prm.n + 1)) return r;
-    c->offset = offset;
-    c->has_key = true;
-    c->has_ksk = d_ksk != nullptr;
-    return 0;
+    const int r = upload_key_device(c, c->devs[dev], d_bsk, true, d_ksk, true, (size_t)c->prm.n + 1);
+    if (!r) c->offset = offset;
+    refresh_key_flags(c);
+    return r;
 }
 
 
@@ -481,6 +509,7 @@ int tfhe_b200_keygen(tfhe_b200_ctx *c, const uint32_t *key_lv0, const uint32_t *
         CU(c, cudaMalloc(&d_s1, (size_t)kN * 4));
         CU(c, cudaMemcpyAsync(d_s0, key_lv0, (size_t)p.n * 4, cudaMemcpyHostToDevice, d.stream));
         CU(c, cudaMemcpyAsync(d_s1, key_lv1, (size_t)kN * 4, cudaMemcpyHostToDevice, d.stream));
+        d.has_key = d.has_ksk = false;
         if (d.bsk) CU(c, cudaFree(d.bsk));
         if (d.bsk_ref) CU(c, cudaFree(d.bsk_ref));
         if (d.ksk) CU(c, cudaFree(d.ksk));
@@ -504,8 +533,8 @@ int tfhe_b200_keygen(tfhe_b200_ctx *c, const uint32_t *key_lv0, const uint32_t *
     uint32_t offset = 0;             // key.genDecompositionOffset (src/key.zig:121-131)
     for (int i = 0; i < p.L; i++) offset += (1u << (p.bgbit - 1)) << (32 - (i + 1) * p.bgbit);
     c->offset = offset;
-    c->has_key = true;
-    c->has_ksk = true;
+    for (Device &d : c->devs) d.has_key = d.has_ksk = true;
+    refresh_key_flags(c);
     return 0;
 }
 
@@ -514,6 +543,7 @@ uint32_t tfhe_b200_decomposition_offset(const tfhe_b200_ctx *c) { return c ? c->
 int tfhe_b200_set_mode(tfhe_b200_ctx *c, int mode) {
     if (!c || (mode != TFHE_B200_MODE_FAST && mode != TFHE_B200_MODE_EXACT)) return fail(c, TFHE_B200_ERR_INVALID, "bad mode");
     c->mode = mode;
+    c->config_epoch++;
     return 0;
 }
 
@@ -915,6 +945,7 @@ int tfhe_b200_sync(tfhe_b200_ctx *c) {
 int tfhe_b200_track_margin(tfhe_b200_ctx *c, int enable) {
     if (!c) return TFHE_B200_ERR_INVALID;
     c->track_margin = enable != 0;
+    c->config_epoch++;
     return 0;
 }
 
@@ -956,6 +987,7 @@ int tfhe_b200_set_tuning(tfhe_b200_ctx *c, const char *key, int value) {
     else if (!strcmp(key, "circuit_lanes")) c->circuit_lanes = value;
     else if (!strcmp(key, "max_chunk")) c->max_chunk = value > 0 ? (size_t)value : c->max_chunk;
     else return fail(c, TFHE_B200_ERR_INVALID, "unknown tuning key %s", key);
+    c->config_epoch++;
     return 0;
 }
 

@@ -21,10 +21,7 @@ constexpr uint64_t kFnvBasis = 0xcbf29ce484222325ull, kFnvPrime = 0x100000001b3u
 
 uint64_t round_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
-bool params_ok(const tfhe_b200_params &p) {
-    return p.N == 1024 && p.n > 0 && p.n <= 4096 && p.L >= 1 && p.L <= 3 && p.bgbit > 0 && p.bgbit * p.L <= 32 && p.basebit > 0 &&
-           p.basebit <= 8 && p.iks_t > 0 && p.basebit * p.iks_t <= 32;
-}
+bool params_ok(const tfhe_b200_params &p) { return params_supported(p); }
 
 uint64_t header_sum(const Header &h) { return checksum(&h, offsetof(Header, header_checksum)); }
 

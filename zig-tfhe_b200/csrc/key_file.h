@@ -34,6 +34,14 @@ struct View {                   // a mapped, validated file
     const uint32_t *ksk = nullptr;   // nullptr when the file has none
 };
 
+// The one parameter validator (tfhe_b200_create and the key-file calls): N = 1024; n + 1 padded to a multiple of 4 must fit
+// the key-switch kernel's 320 threads x 4 columns (n <= 1279; the reference's largest set has n = 1160); 1 + basebit * t <= 32
+// keeps K2's precision offset 2^(31 - basebit * t) defined (src/trgsw.zig:483).
+inline bool params_supported(const tfhe_b200_params &p) {
+    return p.N == 1024 && p.n >= 1 && p.n <= 1279 && p.L >= 1 && p.L <= 4 && p.bgbit >= 1 && p.L * p.bgbit <= 32 && p.basebit >= 1 &&
+           p.basebit <= 8 && p.iks_t >= 1 && 1 + p.basebit * p.iks_t <= 32;
+}
+
 uint64_t checksum(const void *data, size_t bytes);
 uint64_t bsk_bytes(const tfhe_b200_params &p);
 uint64_t ksk_bytes(const tfhe_b200_params &p);

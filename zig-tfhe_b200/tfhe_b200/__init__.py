@@ -320,10 +320,11 @@ class Context:
             self._check(self.lib.tfhe_b200_gate_batch_ops(self.h, _ptr(ops), _ptr(a), _ptr(b), _ptr(out), B))
         return out
 
-    def bootstrap_batch(self, ct, testvec=None, tv_per_item=False):
+    def bootstrap_batch(self, ct, testvec=None, tv_per_item=False, out=None):
         w = self.n + 1
         ct = _u32(ct, w); B = ct.shape[0]
-        out = np.empty((B, w), np.uint32)
+        if out is None:
+            out = np.empty((B, w), np.uint32)
         tv = _u32(testvec) if testvec is not None else None
         self._check(self.lib.tfhe_b200_bootstrap_batch(self.h, _ptr(ct), _ptr(out), B, _ptr(tv), 1 if tv_per_item else 0))
         return out
