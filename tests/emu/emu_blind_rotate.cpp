@@ -11,6 +11,7 @@
 #include <cstring>
 #include <vector>
 
+#include "../../zig-tfhe_b200/csrc/exact_fft.cuh"
 #include "../../zig-tfhe_b200/csrc/host_tables.h"
 #include "../../zig-tfhe_b200/csrc/negacyclic_fft.cuh"
 
@@ -187,6 +188,159 @@ void emu_blind_rotate(int n, int L, int bgbit, uint32_t offset, const uint32_t *
         out_trlwe[kN + j] = G.acc_b[acc_pos(j)];
     }
     if (margin_out) *margin_out = margin;
+}
+
+
+// ---- exact mode (blind_rotate_exact.cu, exact_fft.cuh): the reference DAG, three radix-2 stages per register pass ----
+
+// reference CloudKey.bootstrapping_key -> exact-mode device layout [n*2L][ab][j0][t] cplx, times 2^-10
+void emu_permute_bsk_exact(const double *ref, int n, int L, double *out) {
+    cplx *o = reinterpret_cast<cplx *>(out);
+    for (size_t c = 0; c < (size_t)n * 2 * L; c++)
+        for (int ab = 0; ab < 2; ab++) {
+            const double *src = ref + (c * 2 + ab) * kN;
+            for (int j0 = 0; j0 < 8; j0++)
+                for (int t = 0; t < 64; t++) {
+                    const int j = exact_bin(j0, t);
+                    o[c * kBskChunkCplx + bsk_slot(ab, j0, t)] = cplx{src[j] * (1.0 / 1024.0), src[kHalfN + j] * (1.0 / 1024.0)};
+                }
+        }
+}
+
+int emu_exact_tables_conjugate() {
+    std::vector<double> tab(6 * 512);
+    make_exact_tables(tab.data());
+    return exact_tables_conjugate(tab.data()) ? 1 : 0;
+}
+
+}  // extern "C"
+
+namespace {
+struct ExGroup {
+    uint32_t acc_a[kN], acc_b[kN];
+    cplx x1[kX1Slots], x2[kX2Slots];
+    cplx twist[512];            // acc_pos order
+    cplx twa[kExactPassATw];
+    ExTw twb[64], twc[64];      // per thread
+    ExGroup() {
+        std::vector<double> tab(6 * 512);
+        make_exact_tables(tab.data());
+        make_exact_shared_tables(tab.data(), twist, twa);
+        for (int t = 0; t < 64; t++) {
+            twb[t] = ex_twiddles_b(tab.data() + 2 * 512, tab.data() + 3 * 512, t & 7);
+            twc[t] = ex_twiddles_c(tab.data() + 2 * 512, tab.data() + 3 * 512, 8 * (t & 7) + (t >> 3));
+        }
+    }
+};
+
+// role A registers in (input-digit order) -> role C registers out (position order = bins 64 j0 + 8 lo + hi)
+template <bool CONJ>
+void ex_transform_all(ExGroup &G, cplx (*v)[8]) {
+    for (int t = 0; t < 64; t++) {
+        const int hi = t >> 3, lo = t & 7;
+        ex_pass_a<CONJ>(v[t], G.twa);
+        for (int q = 0; q < 8; q++) G.x1[x1_slot(hi, q, lo)] = v[t][q];
+    }
+    for (int t = 0; t < 64; t++) {
+        const int hi = t >> 3, lo = t & 7;
+        for (int q = 0; q < 8; q++) v[t][q] = G.x1[x1_slot(hi, lo, q)];
+        ex_pass<CONJ>(v[t], G.twb[t].wa, G.twb[t].wb, G.twb[t].wc);
+    }
+    for (int t = 0; t < 64; t++) {
+        const int hi = t >> 3, lo = t & 7;
+        for (int q = 0; q < 8; q++) G.x2[x2_slot(lo, q, hi)] = v[t][q];
+    }
+    for (int t = 0; t < 64; t++) {
+        const int hi = t >> 3, lo = t & 7;
+        for (int q = 0; q < 8; q++) v[t][q] = G.x2[x2_slot(hi, lo, q)];
+        ex_pass<CONJ>(v[t], G.twc[t].wa, G.twc[t].wb, G.twc[t].wc);
+    }
+}
+}  // namespace
+
+extern "C" {
+
+// forward transform alone: poly[1024] signed -> out[1024] doubles in the REFERENCE layout (re | im), times 1/2
+void emu_exact_forward(const int32_t *poly, double *out) {
+    static ExGroup G;
+    static cplx v[64][8];
+    for (int t = 0; t < 64; t++)
+        for (int p = 0; p < 8; p++) {
+            const int e = 64 * p + 8 * (t & 7) + (t >> 3);
+            v[t][p] = ex_twist((double)poly[e], (double)poly[e + kHalfN], G.twist[64 * p + t]);
+        }
+    ex_transform_all<false>(G, v);
+    for (int t = 0; t < 64; t++)
+        for (int j0 = 0; j0 < 8; j0++) {
+            out[exact_bin(j0, t)] = v[t][j0].re;
+            out[kHalfN + exact_bin(j0, t)] = v[t][j0].im;
+        }
+}
+
+void emu_blind_rotate_exact(int n, int L, int bgbit, uint32_t offset, const uint32_t *lin, const double *bskx,
+                            const uint32_t *testvec, uint32_t *out_trlwe, uint32_t *trace) {
+    static ExGroup G;
+    const cplx *bsk = reinterpret_cast<const cplx *>(bskx);
+    const uint32_t mask = (1u << bgbit) - 1u, half_bg = 1u << (bgbit - 1);
+    std::vector<int> atil(n + 1);
+    for (int i = 0; i <= n; i++) {
+        const uint32_t m = (uint32_t)(((uint64_t)lin[i] + (1u << 20)) >> 21);
+        atil[i] = (i == n) ? (2 * kN - (int)m) : (int)m;
+    }
+    const int btil = atil[n];
+    for (int j = 0; j < kN; j++) {
+        const int u = (j - btil) & (2 * kN - 1);
+        const uint32_t va = testvec ? testvec[u & (kN - 1)] : 0u;
+        const uint32_t vb = testvec ? testvec[kN + (u & (kN - 1))] : 0x20000000u;
+        G.acc_a[acc_pos(j)] = (u & kN) ? 0u - va : va;
+        G.acc_b[acc_pos(j)] = (u & kN) ? 0u - vb : vb;
+    }
+    static cplx v[64][8], oa[64][8], ob[64][8];
+    for (int i = 0; i < n; i++) {
+        std::memset(oa, 0, sizeof(oa));
+        std::memset(ob, 0, sizeof(ob));
+        for (int h = 0; h < 2; h++) {
+            const uint32_t *accp = h ? G.acc_b : G.acc_a;
+            static uint32_t d[64][16];
+            for (int t = 0; t < 64; t++) load_rot_diffs(d[t], accp, atil[i], offset, t >> 3, t & 7);
+            for (int l = 0; l < L; l++) {
+                const int sh = 32 - (l + 1) * bgbit;
+                for (int t = 0; t < 64; t++)
+                    for (int p = 0; p < 8; p++) {
+                        const double x_re = (double)(int32_t)(((d[t][2 * p] >> sh) & mask) - half_bg);
+                        const double x_im = (double)(int32_t)(((d[t][2 * p + 1] >> sh) & mask) - half_bg);
+                        v[t][p] = ex_twist(x_re, x_im, G.twist[64 * p + t]);
+                    }
+                ex_transform_all<false>(G, v);
+                const cplx *chunk = bsk + ((size_t)i * 2 * L + h * L + l) * kBskChunkCplx;
+                for (int t = 0; t < 64; t++)
+                    for (int q = 0; q < 8; q++) {
+                        ex_mac(oa[t][q], v[t][q], chunk[bsk_slot(0, q, t)]);
+                        ex_mac(ob[t][q], v[t][q], chunk[bsk_slot(1, q, t)]);
+                    }
+            }
+        }
+        for (int h = 0; h < 2; h++) {
+            cplx(*o)[8] = h ? ob : oa;
+            uint32_t *accp = h ? G.acc_b : G.acc_a;
+            ex_transform_all<true>(G, o);
+            for (int t = 0; t < 64; t++)
+                for (int p = 0; p < 8; p++) {
+                    const cplx r = ex_untwist(o[t][p], G.twist[64 * p + t]);
+                    accp[64 * p + t] += ex_round_torus(r.re);
+                    accp[64 * p + t + kHalfN] += ex_round_torus(r.im);
+                }
+        }
+        if (trace)
+            for (int j = 0; j < kN; j++) {
+                trace[(size_t)i * 2 * kN + j] = G.acc_a[acc_pos(j)];
+                trace[(size_t)i * 2 * kN + kN + j] = G.acc_b[acc_pos(j)];
+            }
+    }
+    for (int j = 0; j < kN; j++) {
+        out_trlwe[j] = G.acc_a[acc_pos(j)];
+        out_trlwe[kN + j] = G.acc_b[acc_pos(j)];
+    }
 }
 
 }  // extern "C"

@@ -71,3 +71,33 @@ def test_emulated_lut_rotation(emu, orc128, keys128):
     out = np.empty((2, 1024), np.uint32)
     emu.emu_blind_rotate(orc128.n, orc128.L, orc128.bgbit, C.c_uint32(keys128.offset), ptr(ct), ptr(bskp), ptr(tv), 0, ptr(out), None, None)
     assert (out == ref).all()
+
+
+def test_exact_tables_are_conjugate_and_exact_forward_matches_oracle(emu):
+    """exact_fft.cuh: the register-blocked exact transform (three radix-2 stages per pass, bit reversal as register
+    naming) returns the reference's forward spectrum bit for bit (the reference's x2 aside, an exact power of two)"""
+    assert emu.emu_exact_tables_conjugate() == 1
+    rng = np.random.default_rng(3)
+    for lo, hi in ((-32, 32), (-2**21, 2**21), (-2**31, 2**31)):
+        poly = rng.integers(lo, hi, 1024).astype(np.int32)
+        out = np.empty(1024, np.float64)
+        emu.emu_exact_forward(ptr(poly), ptr(out))
+        assert (out * 2.0 == O.ifft1024(poly.view(np.uint32))).all()
+
+
+@pytest.mark.parametrize("name,modulus", [("uint4", 16), ("uint1", 2), ("uint2", 4), ("128", 4)])
+def test_emulated_exact_blind_rotation_is_bit_exact(emu, name, modulus):
+    """exact-mode arithmetic (same __host__ __device__ code as blind_rotate_exact_rb_kernel) == oracle on every coefficient
+    of every iteration, on the large-digit sets where the fast transform rounds differently"""
+    orc = O.Oracle(name); keys = keys_for(name, with_ksk=(name == "128"))
+    bskx = np.empty(orc.bsk_len, np.float64)
+    emu.emu_permute_bsk_exact(ptr(keys.bsk), orc.n, orc.L, ptr(bskx))
+    msgs = np.array([3 % modulus, 1], np.uint32)
+    ct = orc.encrypt_lwe_messages(msgs, modulus, keys, seed=5)
+    tv = orc.lut_generate(np.array([(x * x + 1) % modulus for x in range(modulus)], np.uint32), modulus)
+    for i in range(2):
+        ref, tr = orc.blind_rotate(ct[i], keys, testvec=tv, trace=True)
+        out = np.empty((2, 1024), np.uint32); tre = np.empty((orc.n, 2, 1024), np.uint32)
+        emu.emu_blind_rotate_exact(orc.n, orc.L, orc.bgbit, C.c_uint32(keys.offset), ptr(ct[i]), ptr(bskx), ptr(tv), ptr(out), ptr(tre))
+        assert (tre == tr).all(), "first differing iteration %d" % next(j for j in range(orc.n) if (tre[j] != tr[j]).any())
+        assert (out == ref).all()

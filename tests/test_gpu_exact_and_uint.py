@@ -113,3 +113,37 @@ def test_largest_lwe_dimension_set_fast_mode_runs():
         assert out.shape == (5, 2, 1024)
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("name,modulus", [("uint4", 16), ("uint1", 2)])
+def test_exact_register_blocked_equals_legacy_and_oracle(name, modulus):
+    """the register-blocked exact kernel (default) at every CTA width, across a wave boundary, against the round-1
+    one-CTA-per-ciphertext kernel and the oracle"""
+    import tfhe_b200
+    c, orc, k = _ctx(name, tfhe_b200.MODE_EXACT)
+    try:
+        B = 148 * 4 + 9
+        rng = np.random.default_rng(2)
+        msgs = rng.integers(0, modulus, B).astype(np.uint32)
+        ct = orc.encrypt_lwe_messages(msgs, modulus, k, seed=8)
+        tv = orc.lut_generate(np.array([(3 * x + 1) % modulus for x in range(modulus)], np.uint32), modulus)
+        got = c.blind_rotate_batch(ct, tv)
+        sel = np.array([0, 1, 2, 3, 4, 147, 148, 591, 592, 593, B - 1])
+        assert (got[sel] == orc.blind_rotate_batch(ct[sel], k, tv)).all()
+        c.set_tuning("exact_legacy", 1)
+        legacy = c.blind_rotate_batch(ct, tv)
+        c.set_tuning("exact_legacy", 0)
+        assert (got == legacy).all()
+        for kct in (1, 2, 3, 4):
+            c.set_tuning("exact_kct", kct)
+            assert (c.blind_rotate_batch(ct[:23], tv) == got[:23]).all(), kct
+        c.set_tuning("exact_kct", 0)
+        c.track_margin(True)
+        assert (c.blind_rotate_batch(ct[:9], tv) == got[:9]).all()
+        assert c.max_round_margin() > 0.0
+        c.track_margin(False)
+        # per-item test vectors + extraction + key switch through the same kernel
+        tvs = np.stack([orc.lut_generate(np.array([(x + s) % modulus for x in range(modulus)], np.uint32), modulus) for s in range(12)])
+        assert (c.bootstrap_batch(ct[:12], tvs, tv_per_item=True) == orc.bootstrap_batch(ct[:12], k, tvs, tv_per_item=True)).all()
+    finally:
+        c.close()

@@ -30,6 +30,7 @@
 #include <algorithm>
 
 #include "br_common.cuh"
+#include "br_ring.cuh"
 #include "kernels.cuh"
 #include "negacyclic_fft.cuh"
 
@@ -41,42 +42,6 @@ namespace {
 // not shared-memory-bound: 88.8 k vs 90.8 k bootstraps/s at KCT = 4, 83.9 k at KCT = 6 with shared-memory twiddles
 // (profiles/r01_team_probe.log, r01_wave_scaling.log).  The default stays one ciphertext per warp pair, KCT = 4.
 constexpr bool kUnrollL3 = true;   // L = 3 / BGBIT = 6 instantiation of the throughput kernel (false: generic kernel only, for A/B runs)
-constexpr int kMaxStages = 4;  // deepest key ring (16 KiB per stage); Layout<KCT>::kStages picks the depth
-
-// Key-ring producer state, live only in thread 0 of the CTA (see header comment).
-struct Producer {
-    const cplx *src;      // next chunk in global memory
-    cplx *ring;
-    uint64_t *full_bar, *empty_bar;
-    int remaining;        // chunks still to issue
-    int issued;           // chunks issued so far (the first `stages` need no empty wait)
-    int stages;
-    uint64_t policy;      // L2 evict_last for the key stream
-    int stage;
-    uint32_t phase;
-    bool active;
-};
-__device__ __forceinline__ void producer_poll(Producer &pr) {
-    if (pr.active && pr.remaining > 0) {
-        if (pr.issued < pr.stages || mbar_test_wait(&pr.empty_bar[pr.stage], pr.phase ^ 1)) {
-            mbar_arrive_expect_tx(&pr.full_bar[pr.stage], kBskChunkBytes);
-            bulk_g2s(pr.ring + pr.stage * kBskChunkCplx, pr.src, kBskChunkBytes, &pr.full_bar[pr.stage], pr.policy);
-            pr.src += kBskChunkCplx;
-            pr.remaining--;
-            pr.issued++;
-            if (++pr.stage == pr.stages) { pr.stage = 0; pr.phase ^= 1; }
-        }
-    }
-}
-
-// Per-group exchange state.  X2 is double-buffered when DBX2 (one named barrier per transform instead
-// of two): a writer of buffer b at transform k has passed the barrier of transform k-1, which every
-// reader of b at transform k-2 reached only after finishing its reads.
-struct Xbuf {
-    cplx *x1;
-    cplx *x2;     // two consecutive buffers of kX2Slots when double-buffered
-    int flip;     // 0 or kX2Slots
-};
 
 // Twiddles r^1..r^7 of one thread for one pass.  MODE 0: all seven resident (28 registers, KCT <= 4);
 // MODE 1: r, r^2, r^4 resident and the rest expanded per pass (12 registers); MODE 2: read from a shared-memory
@@ -200,8 +165,6 @@ __device__ __forceinline__ void round_accumulate(const cplx (&v)[8], uint32_t *a
         accp[e + kHalfN] += r1;
     }
 }
-
-__host__ __device__ constexpr int align16(int x) { return (x + 15) & ~15; }
 
 // shared-memory footprint of one ciphertext group
 template <int KCT, int TEAM = 1>

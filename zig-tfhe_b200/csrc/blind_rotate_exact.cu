@@ -11,15 +11,24 @@
 //   fmaInFd1024: res += (a_re*b_re - a_im*b_im) * 0.5, rows in order       src/trgsw.zig:139-142, 157-189
 //   fft1024   : x0.5, inverse radix-2, untwist, x(1/512), @round (half away from zero),
 //               i64 -> truncating i32                                      src/fft.zig:370-443
-// The bootstrapping key is used in the reference's own layout and scaling (no permutation).
 //
-// One CTA of 256 threads per ciphertext, one radix-2 butterfly per thread per stage.  This is the
-// parity path, not the throughput path: it exists so that "GPU == reference" can be demonstrated on
-// every parameter set; the fast kernel is the product path wherever it is bit-identical.
+// Two kernels produce those bits:
+//  * blind_rotate_exact_rb_kernel ("register-blocked", the default): the same radix-2 butterflies, three stages at a
+//    time on 8 points in one thread's registers (exact_fft.cuh), 64 threads per ciphertext, KCT ciphertexts per CTA
+//    sharing the key ring -- the geometry of the fast kernel (same exchanges, accumulator layout, cp.async.bulk ring),
+//    only the arithmetic inside each pass differs.  The key is read in the exact chunk layout (permuted, times 2^-10).
+//  * blind_rotate_exact_kernel (round 1, "legacy"): one CTA of 256 threads per ciphertext, one butterfly per thread per
+//    stage through shared memory, key in the reference's own layout.  Kept for A/B runs (tuning key "exact_legacy") and
+//    as the fallback if the host libm's stage tables are not conjugate-symmetric.
 #include <cuda_runtime.h>
 
 #include "br_common.cuh"
+#include "br_ring.cuh"
+#include "exact_fft.cuh"
+#include "host_tables.h"
 #include "kernels.cuh"
+
+#include <vector>
 
 namespace tfhe_b200 {
 
@@ -173,12 +182,237 @@ __global__ void __launch_bounds__(kThreads, 2) blind_rotate_exact_kernel(const B
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Register-blocked exact kernel.
+struct ExactConsts {
+    cplx twa2, twa4, twa5, twa6;     // the pass-A twiddles that are not (1, 0): stage-table entries 2, 4, 5, 6 (kernel
+                                     // parameters live in the constant bank, so they cost no registers)
+};
+
+template <bool CONJ, bool USE_TMA>
+__device__ __forceinline__ void ex_transform(cplx (&v)[8], Xbuf &xb, const ExTw &twb, const ExTw &twc, const ExactConsts &kc, int hi, int lo,
+                                             int barid, Producer &pr) {
+    {
+        const cplx twa[kExactPassATw] = {cplx{1.0, 0.0}, cplx{1.0, 0.0}, kc.twa2, cplx{1.0, 0.0}, kc.twa4, kc.twa5, kc.twa6};
+        ex_pass_a<CONJ>(v, twa);
+    }
+    cplx *x1 = xb.x1;
+#pragma unroll
+    for (int q = 0; q < 8; q++) x1[x1_slot(hi, q, lo)] = v[q];
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; q++) v[q] = x1[x1_slot(hi, lo, q)];
+    ex_pass<CONJ>(v, twb.wa, twb.wb, twb.wc);
+    if (USE_TMA) producer_poll(pr);
+    cplx *x2 = xb.x2 + xb.flip;      // double-buffered: one named barrier per transform (see Xbuf)
+    xb.flip ^= kX2Slots;
+#pragma unroll
+    for (int q = 0; q < 8; q++) x2[x2_slot(lo, q, hi)] = v[q];
+    bar_sync(barid, kGroupThreads);
+#pragma unroll
+    for (int q = 0; q < 8; q++) v[q] = x2[x2_slot(hi, lo, q)];
+    ex_pass<CONJ>(v, twc.wa, twc.wb, twc.wc);
+}
+
+constexpr int kExStages = 3;
+__host__ __device__ constexpr int ex_group_bytes(int n) { return 2 * kN * 4 + kX1Slots * 16 + 2 * kX2Slots * 16 + align16((n + 1) * 2); }
+__host__ __device__ constexpr int ex_fixed_bytes() { return kExStages * kBskChunkBytes + 80 + kExactSharedTabCplx * 16; }
+
+template <int KCT, bool MARGIN>
+__global__ void __launch_bounds__(KCT * kGroupThreads, 1)
+    blind_rotate_exact_rb_kernel(const BrArgs P, const double *__restrict__ tables, const cplx *__restrict__ bsk_x,
+                                 const cplx *__restrict__ shared_tab, const ExactConsts kc) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char *ptr = smem_raw;
+    cplx *bsk_ring = reinterpret_cast<cplx *>(ptr);
+    ptr += kExStages * kBskChunkBytes;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(ptr);
+    uint64_t *empty_bar = full_bar + kMaxStages;
+    ptr += 80;
+    cplx *twist = reinterpret_cast<cplx *>(ptr);     // [512] in acc_pos order
+    ptr += kExactSharedTabCplx * 16;
+    const int n = P.n, L = P.L, bgbit = P.bgbit;
+    const int tid = threadIdx.x;
+    const int first_ct = blockIdx.x * KCT;
+    const int n_active = min(KCT, (int)P.B - first_ct);
+    if (tid == 0) {
+        for (int s = 0; s < kExStages; s++) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], n_active * 2);   // one arrival per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    for (int j = tid; j < kExactSharedTabCplx; j += KCT * kGroupThreads) twist[j] = shared_tab[j];
+    __syncthreads();
+    const int g = tid >> 6, t = tid & 63;
+    if (g >= n_active) return;     // whole warps
+    const int hi = t >> 3, lo = t & 7;
+    const int barid = 1 + g;
+    unsigned char *gb = ptr + (size_t)g * ex_group_bytes(n);
+    uint32_t *acc_a = reinterpret_cast<uint32_t *>(gb), *acc_b = acc_a + kN;
+    Xbuf xb;
+    xb.x1 = reinterpret_cast<cplx *>(gb + 2 * kN * 4);
+    xb.x2 = xb.x1 + kX1Slots;
+    xb.flip = 0;
+    uint16_t *atil = reinterpret_cast<uint16_t *>(gb + 2 * kN * 4 + kX1Slots * 16 + 2 * kX2Slots * 16);
+    const size_t ct = (size_t)P.ct_base + first_ct + g;
+
+    // per-thread stage twiddles (forward table; the inverse direction uses their exact conjugates)
+    const ExTw twb = ex_twiddles_b(tables + 2 * kExactTabStride, tables + 3 * kExactTabStride, lo);
+    const ExTw twc = ex_twiddles_c(tables + 2 * kExactTabStride, tables + 3 * kExactTabStride, 8 * lo + hi);
+
+    {   // gate linear part (gates.zig:48-121) + modulus switch (trgsw.zig:297,312)
+        const GateOperands go = gate_operands(P, ct, n);
+        const int op = go.op;
+        for (int i = t; i <= n; i += kGroupThreads) {
+            uint32_t lin = gate_linear_signed(go, i);
+            if (i == n) lin += gate_constant(op);
+            const uint32_t m = (uint32_t)(((unsigned long long)lin + (1u << 20)) >> 21);
+            atil[i] = (uint16_t)((i == n) ? (2 * kN - m) : m);
+        }
+    }
+    bar_sync(barid, kGroupThreads);
+    {   // acc = X^btil * testvec (trgsw.zig:300-306), acc_pos order
+        const int btil = atil[n];
+        const uint32_t *tv = P.testvec ? P.testvec + (P.tv_per_item ? ct * (size_t)(2 * kN) : 0) : nullptr;
+        for (int j = t; j < kN; j += kGroupThreads) {
+            const int u = (j - btil) & (2 * kN - 1);
+            const uint32_t va = tv ? tv[u & (kN - 1)] : 0u;
+            const uint32_t vb = tv ? tv[kN + (u & (kN - 1))] : 0x20000000u;
+            acc_a[acc_pos(j)] = (u & kN) ? 0u - va : va;
+            acc_b[acc_pos(j)] = (u & kN) ? 0u - vb : vb;
+        }
+    }
+    bar_sync(barid, kGroupThreads);
+
+    const uint32_t mask = (1u << bgbit) - 1u, half_bg = 1u << (bgbit - 1);
+    const uint32_t offset = P.offset;
+    int stage = 0;
+    uint32_t phase = 0;
+    double margin = 0.0;
+    Producer pr;
+    pr.src = bsk_x; pr.ring = bsk_ring; pr.full_bar = full_bar; pr.empty_bar = empty_bar;
+    pr.remaining = n * 2 * L; pr.issued = 0; pr.stage = 0; pr.phase = 0; pr.stages = kExStages;
+    pr.active = tid == 0;
+    pr.policy = pr.active ? l2_policy_evict_last() : 0;
+#pragma unroll
+    for (int s = 0; s < kExStages; s++) producer_poll(pr);
+    __nanosleep((blockIdx.x % 41u) * 128u);   // de-synchronise the CTAs of a wave (see blind_rotate.cu)
+
+    for (int i = 0; i < n; i++) {
+        const int at = atil[i];
+        cplx oa[8], ob[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) { oa[q] = cplx{0.0, 0.0}; ob[q] = cplx{0.0, 0.0}; }
+#pragma unroll 1
+        for (int h = 0; h < 2; h++) {
+            const uint32_t *accp = h ? acc_b : acc_a;
+            uint32_t d[16];
+            load_rot_diffs(d, accp, at, offset, hi, lo);
+#pragma unroll 1
+            for (int l = 0; l < L; l++) {
+                const int sh = 32 - (l + 1) * bgbit;
+                cplx v[8];
+#pragma unroll
+                for (int p = 0; p < 8; p++) {     // decomposition digit (trgsw.zig:208-217), fold + twist (fft.zig:297-334)
+                    const double x_re = (double)(int32_t)(((d[2 * p] >> sh) & mask) - half_bg);
+                    const double x_im = (double)(int32_t)(((d[2 * p + 1] >> sh) & mask) - half_bg);
+                    v[p] = ex_twist(x_re, x_im, twist[64 * p + t]);
+                }
+                ex_transform<false, true>(v, xb, twb, twc, kc, hi, lo, barid, pr);
+                while (!mbar_try_wait(&full_bar[stage], phase)) producer_poll(pr);
+                const cplx *chunk = bsk_ring + stage * kBskChunkCplx;
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    ex_mac(oa[q], v[q], chunk[bsk_slot(0, q, t)]);
+                    ex_mac(ob[q], v[q], chunk[bsk_slot(1, q, t)]);
+                }
+                __syncwarp();
+                if ((tid & 31) == 0) mbar_arrive(&empty_bar[stage]);
+                if (++stage == kExStages) { stage = 0; phase ^= 1; }
+            }
+        }
+#pragma unroll 1
+        for (int h = 0; h < 2; h++) {     // fft1024 (fft.zig:370-443) of each output + cmux add-back (trgsw.zig:278-281)
+            uint32_t *accp = h ? acc_b : acc_a;
+            if (h) {
+#pragma unroll
+                for (int q = 0; q < 8; q++) oa[q] = ob[q];
+            }
+            ex_transform<true, true>(oa, xb, twb, twc, kc, hi, lo, barid, pr);
+#pragma unroll
+            for (int p = 0; p < 8; p++) {
+                const cplx r = ex_untwist(oa[p], twist[64 * p + t]);
+                double r_re, r_im;
+                const uint32_t u_re = ex_round_torus(r.re, &r_re), u_im = ex_round_torus(r.im, &r_im);
+                if (MARGIN) margin = fmax(margin, fmax(fabs(r.re - r_re), fabs(r.im - r_im)));
+                accp[64 * p + t] += u_re;
+                accp[64 * p + t + kHalfN] += u_im;
+            }
+        }
+        bar_sync(barid, kGroupThreads);   // accumulator complete before the next rotated reads
+    }
+
+    if (P.out_trlwe) {
+        uint32_t *o = P.out_trlwe + ct * (size_t)(2 * kN);
+        for (int j = t; j < kN; j += kGroupThreads) { o[j] = acc_a[acc_pos(j)]; o[kN + j] = acc_b[acc_pos(j)]; }
+    }
+    if (P.out_lv1) {   // sampleExtractIndex(., 0): trlwe.zig:146-162
+        uint32_t *o = P.out_lv1 + ct * (size_t)(kN + 1);
+        for (int j = t; j <= kN; j += kGroupThreads)
+            o[j] = (j == 0) ? acc_a[0] : (j == kN) ? acc_b[0] : 0u - acc_a[acc_pos(kN - j)];
+    }
+    if (MARGIN && P.margin_bits) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) margin = fmax(margin, __shfl_xor_sync(0xffffffffu, margin, s));
+        if ((tid & 31) == 0) atomicMax(P.margin_bits, (unsigned long long)__double_as_longlong(margin));
+    }
+}
+
+template <int KCT>
+cudaError_t launch_rb(const BrArgs &a, const ExactArgs &x, const ExactConsts &kc, bool margin, cudaStream_t s) {
+    const size_t smem = ex_fixed_bytes() + (size_t)KCT * ex_group_bytes(a.n);
+    auto k0 = blind_rotate_exact_rb_kernel<KCT, false>;
+    auto k1 = blind_rotate_exact_rb_kernel<KCT, true>;
+    cudaError_t e = cudaFuncSetAttribute(margin ? k1 : k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const unsigned grid = (a.B + KCT - 1) / KCT;
+    if (margin) k1<<<grid, KCT * kGroupThreads, smem, s>>>(a, x.tables, x.bsk_x, x.shared_tab, kc);
+    else k0<<<grid, KCT * kGroupThreads, smem, s>>>(a, x.tables, x.bsk_x, x.shared_tab, kc);
+    return cudaGetLastError();
+}
+
 }  // namespace
 
 // exact_tables: device copy of make_exact_tables() (host_tables.h); bsk_ref: CloudKey.bootstrapping_key as loaded
-cudaError_t launch_blind_rotate_exact(const BrArgs &a, const double *exact_tables, const double *bsk_ref, bool track_margin,
-                                      cudaStream_t s, uint64_t *launches) {
+cudaError_t launch_blind_rotate_exact(const BrArgs &a, const ExactArgs &x, bool track_margin, cudaStream_t s, uint64_t *launches) {
     if (a.B == 0) return cudaSuccess;
+    if (!x.legacy && x.bsk_x && x.shared_tab) {
+        // host copy of the four pass-A twiddles (kernel parameters): regenerated from the same recurrence as the device tables
+        static const ExactConsts kc = [] {
+            std::vector<double> tab(6 * 512);
+            make_exact_tables(tab.data());
+            auto e = [&](int k) { return cplx{tab[2 * 512 + k], tab[3 * 512 + k]}; };
+            return ExactConsts{e(2), e(4), e(5), e(6)};
+        }();
+        const unsigned sms = x.sm_count > 0 ? (unsigned)x.sm_count : 148u;
+        int kct = x.kct;
+        if (kct < 1 || kct > 4) {      // fewest CTA waves; below one wave, the narrowest CTA that still covers the batch
+            kct = 4;
+            for (int k = 1; k <= 4; k++)
+                if ((a.B + sms * k - 1) / (sms * k) <= (a.B + sms * 4 - 1) / (sms * 4)) { kct = k; break; }
+        }
+        if (launches) (*launches)++;
+        switch (kct) {
+            case 1: return launch_rb<1>(a, x, kc, track_margin, s);
+            case 2: return launch_rb<2>(a, x, kc, track_margin, s);
+            case 3: return launch_rb<3>(a, x, kc, track_margin, s);
+            default: return launch_rb<4>(a, x, kc, track_margin, s);
+        }
+    }
+    const double *exact_tables = x.tables, *bsk_ref = x.bsk_ref;
     const size_t smem = (6 * kTabStride + 2 * kHalfN + 2 * kN) * sizeof(double) + 3 * kN * sizeof(uint32_t) + (((size_t)a.n + 1) * 2 + 15) / 16 * 16;
     auto k0 = blind_rotate_exact_kernel<false>;
     auto k1 = blind_rotate_exact_kernel<true>;

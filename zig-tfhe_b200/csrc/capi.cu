@@ -36,7 +36,9 @@ struct Device {
     uint32_t *reenc = nullptr;        // proxy re-encryption key, same device layout as ksk with N -> n
     cplx *tw2 = nullptr, *tw3 = nullptr;
     double *exact_tables = nullptr;   // make_exact_tables(), exact mode
-    double *bsk_ref = nullptr;        // bootstrapping key in the reference layout (exact mode reads it as is)
+    double *bsk_ref = nullptr;        // bootstrapping key in the reference layout (legacy exact kernel, key export)
+    cplx *bsk_x = nullptr;            // bootstrapping key in the exact chunk layout (register-blocked exact kernel)
+    cplx *exact_shared = nullptr;     // make_exact_shared_tables(): twist[512] in acc_pos order + 7 pass-A twiddles
     unsigned long long *margin_bits = nullptr;
     Buf a, b, out, lv1, ops, tv, trlwe, lut;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // K1 start, K1 end / K2 start, K2 end (timing mode)
@@ -64,6 +66,9 @@ struct tfhe_b200_ctx {
     int ks_tile = 0, ks_vec = 0, ks_fill = 0, ks_rot = 0;   // key-switch tuning overrides (0 = automatic)
     size_t max_chunk = (size_t)1 << 18;   // ciphertexts per device per launch
     bool circuit_graph = true;            // replay a circuit's level sequence as one CUDA graph
+    int exact_legacy = 0;                 // 1: round-1 exact kernel (one CTA per ciphertext, shared-memory butterflies)
+    int exact_kct = 0;                    // ciphertexts per CTA of the register-blocked exact kernel (0 = automatic)
+    bool exact_conjugate = true;          // host stage tables are conjugate-symmetric (else the legacy kernel is used)
     int circuit_lanes = 4;                // independent instance groups per device, each on its own stream (set before circuit_create)
     // Bumped by everything a captured circuit graph bakes into its kernel nodes: key buffers (load_key*, keygen), mode,
     // margin tracking, tuning.  A circuit re-captures when its graph was recorded under another epoch.
@@ -147,7 +152,8 @@ int run_device(tfhe_b200_ctx *c, Device &d, int op, const int32_t *d_ops, const 
     d.ev_valid = false;
     if (c->timing) CU(c, cudaEventRecord(d.ev[0], d.stream));
     if (c->mode == TFHE_B200_MODE_EXACT) {
-        CU(c, launch_blind_rotate_exact(A, d.exact_tables, d.bsk_ref, c->track_margin, d.stream, &d.launches));
+        ExactArgs X{d.exact_tables, d.bsk_ref, d.bsk_x, d.exact_shared, (c->exact_legacy || !c->exact_conjugate) ? 1 : 0, c->exact_kct, d.sm_count};
+        CU(c, launch_blind_rotate_exact(A, X, c->track_margin, d.stream, &d.launches));
     } else {
         BrTuning tune = c->tune;
         tune.sm_count = d.sm_count;
@@ -251,6 +257,16 @@ int run_host(tfhe_b200_ctx *c, int op, const int32_t *ops, const uint32_t *a, co
     return 0;
 }
 
+// exact chunk layout of the key on the device, from its reference layout (d.bsk_ref)
+int build_exact_key(tfhe_b200_ctx *c, Device &d) {
+    const tfhe_b200_params &p = c->prm;
+    if (d.bsk_x) { CU(c, cudaFree(d.bsk_x)); d.bsk_x = nullptr; }
+    CU(c, cudaMalloc(&d.bsk_x, (size_t)p.n * 2 * p.L * 2 * kN * 8));
+    CU(c, launch_permute_bsk_exact(d.bsk_ref, d.bsk_x, p.n, p.L, d.stream, &c->launches));
+    CU(c, cudaStreamSynchronize(d.stream));
+    return 0;
+}
+
 // device allocation released on scope exit unless handed over (error paths of the key upload)
 struct DevTmp {
     void *p = nullptr;
@@ -282,6 +298,7 @@ int upload_key_device(tfhe_b200_ctx *c, Device &d, const double *src_bsk, bool b
     d.bsk = (cplx *)fast.release();
     if (d.bsk_ref) CU(c, cudaFree(d.bsk_ref));
     d.bsk_ref = (double *)staging.release();
+    if (int r = build_exact_key(c, d)) return r;
     d.has_key = true;
 
     if (!src_ksk) {
@@ -406,6 +423,9 @@ int tfhe_b200_create(const tfhe_b200_params *params, const int *device_ids, int 
     make_twiddle_tables(tw2, tw3);
     std::vector<double> xt(6 * 512);
     make_exact_tables(xt.data());
+    c->exact_conjugate = exact_tables_conjugate(xt.data());
+    std::vector<cplx> xs(kExactSharedTabCplx + 8);
+    make_exact_shared_tables(xt.data(), xs.data(), xs.data() + kExactSharedTabCplx);
     for (int k = 0; k < n_dev; k++) {
         Device d;
         d.id = device_ids ? device_ids[k] : k;
@@ -423,6 +443,8 @@ int tfhe_b200_create(const tfhe_b200_params *params, const int *device_ids, int 
                   cudaMemcpy(d.tw3, tw3, sizeof(tw3), cudaMemcpyHostToDevice) == cudaSuccess &&
                   cudaMalloc(&d.exact_tables, xt.size() * 8) == cudaSuccess &&
                   cudaMemcpy(d.exact_tables, xt.data(), xt.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
+                  cudaMalloc(&d.exact_shared, xs.size() * sizeof(cplx)) == cudaSuccess &&
+                  cudaMemcpy(d.exact_shared, xs.data(), xs.size() * sizeof(cplx), cudaMemcpyHostToDevice) == cudaSuccess &&
                   cudaMemset(d.margin_bits, 0, 8) == cudaSuccess;
         c->devs.push_back(d);
         if (!ok) {
@@ -439,7 +461,7 @@ void tfhe_b200_destroy(tfhe_b200_ctx *c) {
     for (Device &d : c->devs) {
         cudaSetDevice(d.id);
         if (d.stream) cudaStreamSynchronize(d.stream);
-        for (void *p : {(void *)d.bsk, (void *)d.ksk, (void *)d.reenc, (void *)d.tw2, (void *)d.tw3, (void *)d.exact_tables, (void *)d.bsk_ref, (void *)d.margin_bits, d.a.p, d.b.p,
+        for (void *p : {(void *)d.bsk, (void *)d.ksk, (void *)d.reenc, (void *)d.tw2, (void *)d.tw3, (void *)d.exact_tables, (void *)d.bsk_ref, (void *)d.bsk_x, (void *)d.exact_shared, (void *)d.margin_bits, d.a.p, d.b.p,
                         d.out.p, d.lv1.p, d.ops.p, d.tv.p, d.trlwe.p, d.lut.p})
             if (p) cudaFree(p);
         for (cudaEvent_t e : d.ev) if (e) cudaEventDestroy(e);
@@ -523,6 +545,7 @@ int tfhe_b200_keygen(tfhe_b200_ctx *c, const uint32_t *key_lv0, const uint32_t *
         }
         CU(c, launch_keygen_bsk(d_s0, d_s1, seed, bsk_alpha, p.n, p.L, p.bgbit, d.tw2, d.tw3, d.bsk, d.bsk_ref, d.stream, &c->launches));
         CU(c, launch_keygen_ksk(d_s0, d_s1, seed, ksk_alpha, p.n, p.basebit, p.iks_t, c->ksk_pitch, d.ksk, d_kref, d.stream, &c->launches));
+        if (int r = build_exact_key(c, d)) return r;
         if (k == 0 && bsk_out) CU(c, cudaMemcpyAsync(bsk_out, d.bsk_ref, bsk_doubles * 8, cudaMemcpyDeviceToHost, d.stream));
         if (d_kref) CU(c, cudaMemcpyAsync(ksk_out, d_kref, ksk_ref_words * 4, cudaMemcpyDeviceToHost, d.stream));
         CU(c, cudaStreamSynchronize(d.stream));
@@ -983,6 +1006,8 @@ int tfhe_b200_set_tuning(tfhe_b200_ctx *c, const char *key, int value) {
     else if (!strcmp(key, "ks_vec")) c->ks_vec = value;
     else if (!strcmp(key, "ks_fill")) c->ks_fill = value;
     else if (!strcmp(key, "ks_rot")) c->ks_rot = value;
+    else if (!strcmp(key, "exact_legacy")) c->exact_legacy = value != 0;
+    else if (!strcmp(key, "exact_kct")) c->exact_kct = value;
     else if (!strcmp(key, "circuit_graph")) c->circuit_graph = value != 0;
     else if (!strcmp(key, "circuit_lanes")) c->circuit_lanes = value;
     else if (!strcmp(key, "max_chunk")) c->max_chunk = value > 0 ? (size_t)value : c->max_chunk;

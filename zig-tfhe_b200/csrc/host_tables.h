@@ -4,6 +4,7 @@
 #pragma once
 #include <cmath>
 
+#include "exact_fft.cuh"
 #include "negacyclic_fft.cuh"
 
 namespace tfhe_b200 {
@@ -66,6 +67,24 @@ inline void make_exact_tables(double *out) {
             }
         }
     }
+}
+
+// true when every inverse stage twiddle is the exact conjugate of the forward one (cos even, sin odd in this libm, and
+// the recurrence then conjugates exactly): the register-blocked exact kernel keeps one set of twiddles for both directions
+inline bool exact_tables_conjugate(const double *tab) {
+    const double *fr = tab + 2 * 512, *fi = tab + 3 * 512, *ir = tab + 4 * 512, *ii = tab + 5 * 512;
+    for (int k = 0; k < 511; k++)
+        if (fr[k] != ir[k] || fi[k] != -ii[k]) return false;
+    // the skipped multiplications of pass A rely on these entries being exactly (1, 0)
+    for (int k : {0, 1, 3})
+        if (fr[k] != 1.0 || fi[k] != 0.0) return false;
+    return true;
+}
+
+// shared-memory image of the exact kernel: twist[512] as cplx in acc_pos order + the 7 thread-independent pass-A twiddles
+inline void make_exact_shared_tables(const double *tab, cplx *twist, cplx *twa) {
+    for (int k = 0; k < 512; k++) twist[acc_pos(k)] = cplx{tab[k], tab[512 + k]};
+    for (int k = 0; k < kExactPassATw; k++) twa[k] = cplx{tab[2 * 512 + k], tab[3 * 512 + k]};
 }
 
 }  // namespace tfhe_b200

@@ -45,8 +45,21 @@ struct BrTuning {
 
 // returns cudaSuccess or the launch error; *launches += kernels launched
 cudaError_t launch_blind_rotate(const BrArgs &a, const BrTuning &tune, bool track_margin, cudaStream_t s, uint64_t *launches);
-cudaError_t launch_blind_rotate_exact(const BrArgs &a, const double *exact_tables, const double *bsk_ref, bool track_margin,
-                                      cudaStream_t s, uint64_t *launches);
+// Exact mode.  tables: make_exact_tables() image (6 x 512 doubles); bsk_ref: key in the reference layout (legacy kernel);
+// bsk_x: key in the exact chunk layout (launch_permute_bsk_exact); shared_tab: make_exact_shared_tables() image
+// (512 + 7 cplx).  legacy != 0: the one-CTA-per-ciphertext shared-memory kernel of round 1 (kept for A/B and as the fallback
+// when the host's libm does not give conjugate-symmetric twiddle tables).
+struct ExactArgs {
+    const double *tables;
+    const double *bsk_ref;
+    const cplx *bsk_x;
+    const cplx *shared_tab;
+    int legacy;
+    int kct;        // ciphertexts per CTA (0 = automatic)
+    int sm_count;
+};
+cudaError_t launch_blind_rotate_exact(const BrArgs &a, const ExactArgs &x, bool track_margin, cudaStream_t s, uint64_t *launches);
+cudaError_t launch_permute_bsk_exact(const double *ref_bsk, cplx *out, int n, int L, cudaStream_t s, uint64_t *launches);
 
 // K2: identity key switching, lv1 [B][N+1] -> lv0 [B][n+1].  ksk_dev: [N][t][base-1][pitch] u32.
 struct KsArgs {

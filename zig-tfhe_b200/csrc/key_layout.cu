@@ -2,6 +2,7 @@
 // the leaf order of the radix-8 transform, plus the FP64 roofline microbenchmark.
 #include <cuda_runtime.h>
 
+#include "exact_fft.cuh"
 #include "kernels.cuh"
 #include "negacyclic_fft.cuh"
 
@@ -20,6 +21,18 @@ __global__ void permute_bsk_kernel(const double *__restrict__ in, cplx *__restri
     for (int s = threadIdx.x; s < kHalfN; s += blockDim.x) {
         const int q0 = s >> 6, t = s & 63;
         const int j = leaf_to_ref_bin(t >> 3, t & 7, q0);
+        dst[s] = cplx{src[j] * (1.0 / 1024.0), src[kHalfN + j] * (1.0 / 1024.0)};
+    }
+}
+
+// exact-mode device layout (exact_fft.cuh): out[chunk][ab][j0][t] = reference bin 64 j0 + 8 (t & 7) + (t >> 3), times 2^-10
+__global__ void permute_bsk_exact_kernel(const double *__restrict__ in, cplx *__restrict__ out, size_t polys) {
+    const size_t poly = blockIdx.x;   // chunk * 2 + ab
+    if (poly >= polys) return;
+    const double *src = in + poly * kN;
+    cplx *dst = out + poly * kHalfN;
+    for (int s = threadIdx.x; s < kHalfN; s += blockDim.x) {
+        const int j = exact_bin(s >> 6, s & 63);
         dst[s] = cplx{src[j] * (1.0 / 1024.0), src[kHalfN + j] * (1.0 / 1024.0)};
     }
 }
@@ -57,6 +70,13 @@ __global__ void fp64_peak_kernel(double *sink, int iters, double a, double b) {
 cudaError_t launch_permute_bsk(const double *ref_bsk, cplx *out, int n, int L, cudaStream_t s, uint64_t *launches) {
     const size_t polys = (size_t)n * 2 * L * 2;
     permute_bsk_kernel<<<(unsigned)polys, 256, 0, s>>>(ref_bsk, out, polys);
+    if (launches) (*launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_permute_bsk_exact(const double *ref_bsk, cplx *out, int n, int L, cudaStream_t s, uint64_t *launches) {
+    const size_t polys = (size_t)n * 2 * L * 2;
+    permute_bsk_exact_kernel<<<(unsigned)polys, 256, 0, s>>>(ref_bsk, out, polys);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }
