@@ -263,3 +263,38 @@ def test_split_launch_full_waves_plus_tail(ctx128, orc128, keys128):
     got = ctx128.blind_rotate_batch(ca, tv, tv_per_item=True)
     for i in (0, 591, 592, B - 1):
         assert (got[i] == orc128.blind_rotate_batch(ca[i:i + 1], keys128, tv[i])[0]).all(), i
+
+
+@pytest.mark.parametrize("name", ["128", "80", "110", "uint1"])
+def test_tensor_core_keyswitch_bit_exact(name):
+    """K2t (keyswitch_tc.cu): the key switch as a u8 x u8 -> s32 tcgen05 contraction over one-hot digits, four byte
+    planes recombined mod 2^32 -- integer arithmetic, so the bar is equality with trgsw.identityKeySwitching
+    (src/trgsw.zig:471-502) on every word, at row counts around the 128-row MMA tile and for every column-group width
+    (n + 1 = 551, 631, 701: last groups of 40, 120 and 64 columns)."""
+    import tfhe_b200
+    orc = O.Oracle(name); k = keys_for(name)
+    c = tfhe_b200.Context(name, devices=[0])
+    try:
+        c.load_key(k.bsk, k.ksk, k.offset)
+        rng = np.random.default_rng(5)
+        c.set_tuning("ks_tc", 1)
+        for B in (1, 127, 128, 129, 1000):
+            lv1 = rng.integers(0, 2**32, (B, 1025), dtype=np.uint32)
+            if B == 129:
+                lv1[0] = 0; lv1[1] = 0xFFFFFFFF; lv1[2, :1024] = 0x55555555; lv1[3, :1024] = 0xAAAAAAAA   # digit patterns 0, 3, 1, 2
+            got = c.keyswitch_batch(lv1)
+            ref = orc.keyswitch_batch(lv1, k)
+            assert (got == ref).all(), f"{name}: tensor-core key switch differs at B={B}: rows {np.nonzero((got != ref).any(axis=1))[0][:5]}"
+        c.set_tuning("ks_tc", -1)
+        assert (c.keyswitch_batch(lv1) == ref).all()          # scalar kernel, same bits
+        c.set_tuning("ks_tc", 0)
+        # whole gates through K1 -> K2t (automatic selection from 192 ciphertexts up); uint1's transform is exact only in exact mode
+        if name == "uint1":
+            c.set_mode(tfhe_b200.MODE_EXACT)
+        bits = rng.integers(0, 2, 300).astype(np.uint8)
+        ca = orc.encrypt_bools(bits, k, 1); cb = orc.encrypt_bools(1 - bits, k, 2)
+        out = c.gate_batch(O.NAND, ca, cb)
+        sel = np.arange(0, 300, 13)
+        assert (out[sel] == orc.gate_batch(O.NAND, ca[sel], cb[sel], k)).all()
+    finally:
+        c.close()

@@ -33,6 +33,7 @@ struct Device {
     cudaStream_t stream = nullptr;
     cplx *bsk = nullptr;
     uint32_t *ksk = nullptr;
+    uint8_t *ksk_tc = nullptr;        // key-switching key as tensor-core operand tiles (keyswitch_tc.cu), BASEBIT = 2 sets
     uint32_t *reenc = nullptr;        // proxy re-encryption key, same device layout as ksk with N -> n
     cplx *tw2 = nullptr, *tw3 = nullptr;
     double *exact_tables = nullptr;   // make_exact_tables(), exact mode
@@ -40,7 +41,7 @@ struct Device {
     cplx *bsk_x = nullptr;            // bootstrapping key in the exact chunk layout (register-blocked exact kernel)
     cplx *exact_shared = nullptr;     // make_exact_shared_tables(): twist[512] in acc_pos order + 7 pass-A twiddles
     unsigned long long *margin_bits = nullptr;
-    Buf a, b, out, lv1, ops, tv, trlwe, lut;
+    Buf a, b, out, lv1, ops, tv, trlwe, lut, ksdig;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // K1 start, K1 end / K2 start, K2 end (timing mode)
     bool ev_valid = false;
     uint64_t launches = 0;             // kernels launched on this device by its host thread (summed by tfhe_b200_launch_count)
@@ -64,6 +65,8 @@ struct tfhe_b200_ctx {
     uint64_t launches = 0;
     bool timing = false;
     int ks_tile = 0, ks_vec = 0, ks_fill = 0, ks_rot = 0;   // key-switch tuning overrides (0 = automatic)
+    int ks_tc = 0;                        // tensor-core key switch: 0 = automatic (batches >= ks_tc_min), 1 = always, -1 = never
+    int ks_tc_min = 192;
     size_t max_chunk = (size_t)1 << 18;   // ciphertexts per device per launch
     bool circuit_graph = true;            // replay a circuit's level sequence as one CUDA graph
     int exact_legacy = 0;                 // 1: round-1 exact kernel (one CTA per ciphertext, shared-memory butterflies)
@@ -122,6 +125,25 @@ bool wide_round(const tfhe_b200_params &p) {
     return bits >= 50;
 }
 
+// K2 on device buffers: tensor-core contraction for large batches on the BASEBIT = 2 sets, the scalar kernel otherwise.
+// ks_digits: caller-owned digit scratch (circuit lanes, sized before graph capture) or nullptr -> the device's own.
+int run_keyswitch(tfhe_b200_ctx *c, Device &d, const uint32_t *lv1, uint32_t *lv0, size_t B, uint64_t *ks_digits, uint64_t *launches) {
+    if (B == 0) return 0;
+    KsArgs K{lv1, lv0, d.ksk, (uint32_t)B, c->prm.n, c->prm.basebit, c->prm.iks_t, c->ksk_pitch, kN, c->ks_tile, c->ks_vec};
+    K.fill = c->ks_fill; K.rot = c->ks_rot;
+    const bool tc = d.ksk_tc && c->ks_tc >= 0 && (c->ks_tc > 0 || B >= (size_t)c->ks_tc_min);
+    if (tc) {
+        if (!ks_digits) {
+            if (int r = ensure(c, d.ksdig, B * keyswitch_tc_digit_words(c->prm.iks_t) * 8)) return r;
+            ks_digits = (uint64_t *)d.ksdig.p;
+        }
+        CU(c, launch_keyswitch_tc(K, d.ksk_tc, ks_digits, d.stream, launches));
+    } else {
+        CU(c, launch_keyswitch(K, d.sm_count, d.stream, launches));
+    }
+    return 0;
+}
+
 // K1 (+K2) on device buffers of one device
 struct LevelRef {            // one dependency level of a circuit: operands are wire rows of d_a (see BrArgs)
     const int32_t *ops;
@@ -131,7 +153,7 @@ struct LevelRef {            // one dependency level of a circuit: operands are 
 
 int run_device(tfhe_b200_ctx *c, Device &d, int op, const int32_t *d_ops, const uint32_t *d_a, const uint32_t *d_b, uint32_t *d_lv0,
                uint32_t *d_lv1_out, uint32_t *d_trlwe, size_t B, const uint32_t *d_tv, int tv_per_item,
-               const LevelRef *lvl = nullptr, bool concurrent = false) {
+               const LevelRef *lvl = nullptr, bool concurrent = false, uint64_t *ks_digits = nullptr) {
     if (!c->has_key) return fail(c, TFHE_B200_ERR_NO_KEY, "no cloud key loaded");
     if (B == 0) return 0;
     CU(c, cudaSetDevice(d.id));
@@ -163,9 +185,7 @@ int run_device(tfhe_b200_ctx *c, Device &d, int op, const int32_t *d_ops, const 
     if (c->timing) CU(c, cudaEventRecord(d.ev[1], d.stream));
     if (d_lv0) {
         if (!c->has_ksk) return fail(c, TFHE_B200_ERR_NO_KEY, "no key-switching key loaded");
-        KsArgs K{lv1, d_lv0, d.ksk, (uint32_t)B, c->prm.n, c->prm.basebit, c->prm.iks_t, c->ksk_pitch, kN, c->ks_tile, c->ks_vec};
-        K.fill = c->ks_fill; K.rot = c->ks_rot;
-        CU(c, launch_keyswitch(K, d.sm_count, d.stream, &d.launches));
+        if (int r = run_keyswitch(c, d, lv1, d_lv0, B, ks_digits, &d.launches)) return r;
     }
     if (c->timing) {
         CU(c, cudaEventRecord(d.ev[2], d.stream));
@@ -257,6 +277,17 @@ int run_host(tfhe_b200_ctx *c, int op, const int32_t *ops, const uint32_t *a, co
     return 0;
 }
 
+// tensor-core operand image of the packed key-switching key (d.ksk), on the sets the tensor-core kernel covers
+int build_tc_key(tfhe_b200_ctx *c, Device &d) {
+    const tfhe_b200_params &p = c->prm;
+    if (d.ksk_tc) { CU(c, cudaFree(d.ksk_tc)); d.ksk_tc = nullptr; }
+    if (!keyswitch_tc_supported(p.basebit, p.iks_t, kN, c->ksk_pitch)) return 0;
+    CU(c, cudaMalloc(&d.ksk_tc, keyswitch_tc_key_bytes(c->ksk_pitch, p.iks_t)));
+    CU(c, launch_ksk_to_tc(d.ksk, d.ksk_tc, p.iks_t, c->ksk_pitch, d.stream, &c->launches));
+    CU(c, cudaStreamSynchronize(d.stream));
+    return 0;
+}
+
 // exact chunk layout of the key on the device, from its reference layout (d.bsk_ref)
 int build_exact_key(tfhe_b200_ctx *c, Device &d) {
     const tfhe_b200_params &p = c->prm;
@@ -304,6 +335,7 @@ int upload_key_device(tfhe_b200_ctx *c, Device &d, const double *src_bsk, bool b
     if (!src_ksk) {
         d.has_ksk = false;
         if (d.ksk) { CU(c, cudaFree(d.ksk)); d.ksk = nullptr; }
+        if (d.ksk_tc) { CU(c, cudaFree(d.ksk_tc)); d.ksk_tc = nullptr; }
     } else {
         const int base = 1 << p.basebit;
         const size_t rows = (size_t)kN * p.iks_t * base;
@@ -319,6 +351,7 @@ int upload_key_device(tfhe_b200_ctx *c, Device &d, const double *src_bsk, bool b
         CU(c, cudaStreamSynchronize(d.stream));
         if (d.ksk) CU(c, cudaFree(d.ksk));
         d.ksk = (uint32_t *)packed.release();
+        if (int r = build_tc_key(c, d)) return r;
         d.has_ksk = true;
     }
     return 0;
@@ -346,7 +379,7 @@ struct tfhe_b200_circuit {
         uint32_t *d_a = nullptr, *d_b = nullptr;
         cudaStream_t stream = nullptr;   // lane 0: the device's stream; others: owned
         bool owns_stream = false, owns_tables = false;
-        Buf wires, lv1, neg;
+        Buf wires, lv1, neg, ksdig;
         cudaGraphExec_t graph = nullptr;
         size_t graph_inst = 0;
         uint64_t graph_epoch = 0;        // ctx->config_epoch at capture time
@@ -368,7 +401,7 @@ int circuit_levels(tfhe_b200_ctx *c, tfhe_b200_circuit *q, Device &dev, tfhe_b20
     for (const auto &lv : q->levels) {
         LevelRef ref{pd.d_ops + lv.off, pd.d_a + lv.off, pd.d_b + lv.off, (uint32_t)inst};
         rc = run_device(c, d, 0, nullptr, wires, nullptr, wires + (size_t)lv.first_slot * inst * w0, (uint32_t *)pd.lv1.p, nullptr,
-                        (size_t)lv.G * inst, nullptr, 0, &ref, q->lanes > 1);
+                        (size_t)lv.G * inst, nullptr, 0, &ref, q->lanes > 1, (uint64_t *)pd.ksdig.p);
         if (rc) break;
     }
     dev.launches = d.launches;   // the copy counted them
@@ -461,8 +494,8 @@ void tfhe_b200_destroy(tfhe_b200_ctx *c) {
     for (Device &d : c->devs) {
         cudaSetDevice(d.id);
         if (d.stream) cudaStreamSynchronize(d.stream);
-        for (void *p : {(void *)d.bsk, (void *)d.ksk, (void *)d.reenc, (void *)d.tw2, (void *)d.tw3, (void *)d.exact_tables, (void *)d.bsk_ref, (void *)d.bsk_x, (void *)d.exact_shared, (void *)d.margin_bits, d.a.p, d.b.p,
-                        d.out.p, d.lv1.p, d.ops.p, d.tv.p, d.trlwe.p, d.lut.p})
+        for (void *p : {(void *)d.bsk, (void *)d.ksk, (void *)d.ksk_tc, (void *)d.reenc, (void *)d.tw2, (void *)d.tw3, (void *)d.exact_tables, (void *)d.bsk_ref, (void *)d.bsk_x, (void *)d.exact_shared, (void *)d.margin_bits, d.a.p, d.b.p,
+                        d.out.p, d.lv1.p, d.ops.p, d.tv.p, d.trlwe.p, d.lut.p, d.ksdig.p})
             if (p) cudaFree(p);
         for (cudaEvent_t e : d.ev) if (e) cudaEventDestroy(e);
         if (d.stream) cudaStreamDestroy(d.stream);
@@ -546,6 +579,7 @@ int tfhe_b200_keygen(tfhe_b200_ctx *c, const uint32_t *key_lv0, const uint32_t *
         CU(c, launch_keygen_bsk(d_s0, d_s1, seed, bsk_alpha, p.n, p.L, p.bgbit, d.tw2, d.tw3, d.bsk, d.bsk_ref, d.stream, &c->launches));
         CU(c, launch_keygen_ksk(d_s0, d_s1, seed, ksk_alpha, p.n, p.basebit, p.iks_t, c->ksk_pitch, d.ksk, d_kref, d.stream, &c->launches));
         if (int r = build_exact_key(c, d)) return r;
+        if (int r = build_tc_key(c, d)) return r;
         if (k == 0 && bsk_out) CU(c, cudaMemcpyAsync(bsk_out, d.bsk_ref, bsk_doubles * 8, cudaMemcpyDeviceToHost, d.stream));
         if (d_kref) CU(c, cudaMemcpyAsync(ksk_out, d_kref, ksk_ref_words * 4, cudaMemcpyDeviceToHost, d.stream));
         CU(c, cudaStreamSynchronize(d.stream));
@@ -631,9 +665,7 @@ int tfhe_b200_keyswitch_batch(tfhe_b200_ctx *c, const uint32_t *lv1, uint32_t *l
             if (int r = ensure(c, d.lv1, nb * w1 * 4)) return r;
             if (int r = ensure(c, d.out, nb * w0 * 4)) return r;
             CU(c, cudaMemcpyAsync(d.lv1.p, lv1 + off * w1, nb * w1 * 4, cudaMemcpyHostToDevice, d.stream));
-            KsArgs K{(uint32_t *)d.lv1.p, (uint32_t *)d.out.p, d.ksk, (uint32_t)nb, c->prm.n, c->prm.basebit, c->prm.iks_t, c->ksk_pitch, kN, c->ks_tile, c->ks_vec};
-            K.fill = c->ks_fill; K.rot = c->ks_rot;
-            CU(c, launch_keyswitch(K, d.sm_count, d.stream, &c->launches));
+            if (int r = run_keyswitch(c, d, (uint32_t *)d.lv1.p, (uint32_t *)d.out.p, nb, nullptr, &c->launches)) return r;
             CU(c, cudaMemcpyAsync(lv0 + off * w0, d.out.p, nb * w0 * 4, cudaMemcpyDeviceToHost, d.stream));
             CU(c, cudaStreamSynchronize(d.stream));
         }
@@ -725,10 +757,7 @@ int tfhe_b200_keyswitch_batch_device(tfhe_b200_ctx *c, int dev, const uint32_t *
     if (!c->has_ksk) return fail(c, TFHE_B200_ERR_NO_KEY, "no key-switching key loaded");
     Device &d = c->devs[dev];
     CU(c, cudaSetDevice(d.id));
-    KsArgs K{d_lv1, d_lv0, d.ksk, (uint32_t)B, c->prm.n, c->prm.basebit, c->prm.iks_t, c->ksk_pitch, kN, c->ks_tile, c->ks_vec};
-    K.fill = c->ks_fill; K.rot = c->ks_rot;
-    CU(c, launch_keyswitch(K, d.sm_count, d.stream, &c->launches));
-    return 0;
+    return run_keyswitch(c, d, d_lv1, d_lv0, B, nullptr, &c->launches);
 }
 
 
@@ -856,7 +885,7 @@ void tfhe_b200_circuit_destroy(tfhe_b200_circuit *q) {
         if (pd.owns_tables)
             for (void *p : {(void *)pd.d_ops, (void *)pd.d_a, (void *)pd.d_b})
                 if (p) cudaFree(p);
-        for (void *p : {pd.wires.p, pd.lv1.p, pd.neg.p})
+        for (void *p : {pd.wires.p, pd.lv1.p, pd.neg.p, pd.ksdig.p})
             if (p) cudaFree(p);
         if (pd.owns_stream) cudaStreamDestroy(pd.stream);
     }
@@ -891,10 +920,11 @@ static int circuit_run_device(tfhe_b200_ctx *c, tfhe_b200_circuit *q, int k, con
             const size_t inst = std::min(per_pass, hi[l] - pos[l]);
             cur[l] = inst;
             if (inst == 0) continue;
-            const void *old_w = pd.wires.p, *old_l = pd.lv1.p;
+            const void *old_w = pd.wires.p, *old_l = pd.lv1.p, *old_d = pd.ksdig.p;
             if (int r = ensure(c, pd.wires, q->n_slots * inst * w0 * 4)) return r;
             if (int r = ensure(c, pd.lv1, std::max<size_t>(q->max_width, 1) * inst * w1 * 4)) return r;
-            if ((old_w != pd.wires.p || old_l != pd.lv1.p) && pd.graph) { cudaGraphExecDestroy(pd.graph); pd.graph = nullptr; }
+            if (int r = ensure(c, pd.ksdig, std::max<size_t>(q->max_width, 1) * inst * keyswitch_tc_digit_words(c->prm.iks_t) * 8)) return r;
+            if ((old_w != pd.wires.p || old_l != pd.lv1.p || old_d != pd.ksdig.p) && pd.graph) { cudaGraphExecDestroy(pd.graph); pd.graph = nullptr; }
             uint32_t *wires = (uint32_t *)pd.wires.p;
             for (size_t i = 0; i < q->n_inputs; i++)
                 CU(c, cudaMemcpyAsync(wires + i * inst * w0, inputs + (i * instances + pos[l]) * w0, inst * w0 * 4, cudaMemcpyHostToDevice, pd.stream));
@@ -1006,6 +1036,8 @@ int tfhe_b200_set_tuning(tfhe_b200_ctx *c, const char *key, int value) {
     else if (!strcmp(key, "ks_vec")) c->ks_vec = value;
     else if (!strcmp(key, "ks_fill")) c->ks_fill = value;
     else if (!strcmp(key, "ks_rot")) c->ks_rot = value;
+    else if (!strcmp(key, "ks_tc")) c->ks_tc = value;
+    else if (!strcmp(key, "ks_tc_min")) c->ks_tc_min = value;
     else if (!strcmp(key, "exact_legacy")) c->exact_legacy = value != 0;
     else if (!strcmp(key, "exact_kct")) c->exact_kct = value;
     else if (!strcmp(key, "circuit_graph")) c->circuit_graph = value != 0;

@@ -75,6 +75,15 @@ struct KsArgs {
 };
 cudaError_t launch_keyswitch(const KsArgs &a, int sm_count, cudaStream_t s, uint64_t *launches);
 
+// K2t (keyswitch_tc.cu): the same key switch as an unsigned 8-bit tensor-core contraction (tcgen05.mma kind::i8) over the
+// one-hot expansion of the digits; BASEBIT = 2 sets, in_dim = N.  ksk_tc: launch_ksk_to_tc() image of the packed key
+// (keyswitch_tc_key_bytes()); digits: scratch of B * keyswitch_tc_digit_words() u64.
+bool keyswitch_tc_supported(int basebit, int iks_t, int in_dim, int pitch);
+size_t keyswitch_tc_key_bytes(int pitch, int iks_t);
+size_t keyswitch_tc_digit_words(int iks_t);
+cudaError_t launch_ksk_to_tc(const uint32_t *ksk_packed, uint8_t *out, int iks_t, int pitch, cudaStream_t s, uint64_t *launches);
+cudaError_t launch_keyswitch_tc(const KsArgs &a, const uint8_t *ksk_tc, uint64_t *digits, cudaStream_t s, uint64_t *launches);
+
 // one-time key re-layout kernels
 cudaError_t launch_permute_bsk(const double *ref_bsk, cplx *out, int n, int L, cudaStream_t s, uint64_t *launches);
 cudaError_t launch_repack_ksk(const uint32_t *ref_ksk, size_t ref_row_stride_u32, uint32_t *out, int n, int basebit, int iks_t,
