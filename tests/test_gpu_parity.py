@@ -42,11 +42,15 @@ def test_keyswitch_bit_exact(ctx128, orc128, keys128):
         assert (got == ref).all(), f"key switch differs at B={B}"
 
 
-@pytest.mark.parametrize("use_tma,kct", [(1, 0), (0, 0), (1, 1), (1, 2), (1, 3), (1, 4), (1, 5), (1, 6), (0, 6)])
-def test_blind_rotate_bit_exact(ctx128, orc128, keys128, use_tma, kct):
-    """pre-keyswitch TRLWE coefficients: stated tolerance 0 versus the reference f64 FFT path."""
+@pytest.mark.parametrize("use_tma,kct,twt", [(1, 0, 0), (0, 0, 0), (1, 1, 0), (1, 2, 0), (1, 3, 0), (1, 4, 0), (1, 5, 0), (1, 6, 0), (0, 6, 0),
+                                             (1, 6, -1), (1, 5, -1), (1, 4, 1), (1, 5, 1)])
+def test_blind_rotate_bit_exact(ctx128, orc128, keys128, use_tma, kct, twt):
+    """pre-keyswitch TRLWE coefficients: stated tolerance 0 versus the reference f64 FFT path.  Every CTA width of the
+    throughput kernel, key ring or direct loads, twiddles in registers / expanded / in tensor memory (twt), accumulators
+    in registers or tensor memory (kct 6, twt -1)."""
     ctx128.set_tuning("use_tma", use_tma)
     ctx128.set_tuning("kct", kct)
+    ctx128.set_tuning("twt", twt)
     try:
         B = 13
         _, _, ca, cb = _enc_pairs(orc128, keys128, B, seed=3)
@@ -60,6 +64,7 @@ def test_blind_rotate_bit_exact(ctx128, orc128, keys128, use_tma, kct):
     finally:
         ctx128.set_tuning("use_tma", 1)
         ctx128.set_tuning("kct", 0)
+        ctx128.set_tuning("twt", 0)
 
 
 @pytest.mark.parametrize("op", list(range(10)))

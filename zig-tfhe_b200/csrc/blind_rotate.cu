@@ -36,24 +36,59 @@
 
 namespace tfhe_b200 {
 
+// Diagnostic builds (tools/build_diag.sh, -DTFHE_B200_DIAG): BrArgs.diag switches parts of the throughput kernel OFF to
+// measure what each costs (results are then wrong on purpose).  bit 0: no key ring (no bulk copies, no mbarrier waits);
+// bit 1: no key loads in the pointwise MAC; bit 2: X2 exchange without the group barrier; bit 3: no X1 exchange;
+// bit 4: no X2 exchange; bit 5: the ring runs (bulk copies, releases) but nobody waits for a chunk to land.  The product
+// build compiles none of this.
+#ifdef TFHE_B200_DIAG
+#define DIAG_ON(P, bit) (((P).diag >> (bit)) & 1)
+#else
+#define DIAG_ON(P, bit) 0
+#endif
+
 namespace {
 
 // Teams of two (tuning key "team") cut the shared-memory wavefronts by 11 % (ncu) but the kernel is latency-bound,
 // not shared-memory-bound: 88.8 k vs 90.8 k bootstraps/s at KCT = 4, 83.9 k at KCT = 6 with shared-memory twiddles
 // (profiles/r01_team_probe.log, r01_wave_scaling.log).  The default stays one ciphertext per warp pair, KCT = 4.
+// Key-ring refill policy of the throughput kernel.  true: the consumer warp that releases a stage LAST (a shared-memory
+// counter per stage) issues the next bulk copy into it at once.  false (round 1, -DTFHE_B200_RING_POLL): thread 0 polls
+// the stages' empty barriers at the exchange points of its own transforms -- a stage released just after a poll then
+// waits most of a transform for its refill, and warp 0 runs the divergent poll code on everybody's critical path
+// (profiles/r02_k1_ring.log: same speed at four ciphertexts per CTA, +6 % at six, where three warps per scheduler drift further apart).
+#ifdef TFHE_B200_RING_POLL
+constexpr bool kRingLastArriver = false;
+#else
+constexpr bool kRingLastArriver = true;
+#endif
 constexpr bool kUnrollL3 = true;   // L = 3 / BGBIT = 6 instantiation of the throughput kernel (false: generic kernel only, for A/B runs)
 
 // Twiddles r^1..r^7 of one thread for one pass.  MODE 0: all seven resident (28 registers, KCT <= 4);
 // MODE 1: r, r^2, r^4 resident and the rest expanded per pass (12 registers); MODE 2: read from a shared-memory
 // table right before use (0 registers; with teams of two the loads of adjacent lanes merge, see the kernel).
-constexpr int kTwFull = 0, kTwPow = 1, kTwSmem = 2;
+// MODE 3: the seven twiddles live in 32 tensor-memory columns of this thread's lane (written once at kernel start) and are
+// fetched with one tcgen05.ld right before each pass: 0 registers outside the pass and no shared-memory traffic, which
+// is what lets 5 or 6 ciphertexts (10 / 12 warps at 200 / 168 registers) share an SM without touching the saturated
+// shared-memory pipe (tuning key "twt").
+constexpr int kTwFull = 0, kTwPow = 1, kTwSmem = 2, kTwTmem = 3;
 template <int MODE>
 struct Tw2 {
     cplx w[MODE == kTwFull ? 7 : MODE == kTwPow ? 3 : 1];
     const cplx *tab;   // MODE 2: &table[this thread's node], powers `stride` apart
     int stride;
+    uint32_t taddr;    // MODE 3: tensor-memory address (lane quadrant of this warp, first of 32 columns)
     __device__ __forceinline__ void get(cplx (&out)[7]) const {
-        if (MODE == kTwPow) expand_powers(out, w[0], w[1], w[2]);
+        if (MODE == kTwTmem) {
+            uint32_t r[32];
+            tmem_ld32(taddr, r);
+            tmem_wait_ld();
+#pragma unroll
+            for (int p = 0; p < 7; p++) {
+                out[p].re = __hiloint2double((int)r[4 * p + 1], (int)r[4 * p]);
+                out[p].im = __hiloint2double((int)r[4 * p + 3], (int)r[4 * p + 2]);
+            }
+        } else if (MODE == kTwPow) expand_powers(out, w[0], w[1], w[2]);
         else if (MODE == kTwSmem) {
 #pragma unroll
             for (int p = 0; p < 7; p++) out[p] = tab[p * stride];
@@ -67,28 +102,32 @@ struct Tw2 {
 // forward transform, role A registers in -> role C (leaf order) out
 template <bool USE_TMA, bool DBX2, int POW, int POW3>
 __device__ __forceinline__ void fwd_transform(cplx (&v)[8], Xbuf &xb, const Tw2<POW> &tw2, const Tw2<POW3> &tw3, int hi, int lo,
-                                              int barid, Producer &pr, int nthr = kGroupThreads) {
+                                              int barid, Producer &pr, int nthr = kGroupThreads, int diag = 0) {
     fwd_pass1(v);
     cplx *x1 = xb.x1;
+    if (!(diag & 8)) {
 #pragma unroll
     for (int q = 0; q < 8; q++) x1[x1_slot(hi, q, lo)] = v[q];
     __syncwarp();
 #pragma unroll
     for (int q = 0; q < 8; q++) v[q] = x1[x1_slot(hi, lo, q)];
+    }
     {
         cplx w[7];
         tw2.get(w);
         fwd_pass(v, w, 1);
     }
-    if (USE_TMA) producer_poll(pr);
+    if (USE_TMA && !kRingLastArriver) producer_poll(pr);
     cplx *x2 = xb.x2 + (DBX2 ? xb.flip : 0);
     if (DBX2) xb.flip ^= kX2Slots;
     else bar_sync(barid, nthr);   // every reader of the previous X2 contents is done
+    if (!(diag & 16)) {
 #pragma unroll
     for (int q = 0; q < 8; q++) x2[x2_slot(lo, q, hi)] = v[q];
-    bar_sync(barid, nthr);
+    if (diag & 4) __syncwarp(); else bar_sync(barid, nthr);
 #pragma unroll
     for (int q = 0; q < 8; q++) v[q] = x2[x2_slot(hi, lo, q)];
+    }
     {
         cplx w[7];
         tw3.get(w);
@@ -99,32 +138,36 @@ __device__ __forceinline__ void fwd_transform(cplx (&v)[8], Xbuf &xb, const Tw2<
 // inverse transform, role C (leaf order) in -> role A out: v[p] = c_e, e = 64 p + 8 lo + hi
 template <bool USE_TMA, bool DBX2, int POW, int POW3>
 __device__ __forceinline__ void inv_transform(cplx (&v)[8], Xbuf &xb, const Tw2<POW> &tw2, const Tw2<POW3> &tw3, int hi, int lo,
-                                              int barid, Producer &pr, int nthr = kGroupThreads) {
+                                              int barid, Producer &pr, int nthr = kGroupThreads, int diag = 0) {
     {
         cplx w[7];
         tw3.get(w);
         inv_pass(v, w, 1);
     }
-    if (USE_TMA) producer_poll(pr);
+    if (USE_TMA && !kRingLastArriver) producer_poll(pr);
     cplx *x2 = xb.x2 + (DBX2 ? xb.flip : 0);
     if (DBX2) xb.flip ^= kX2Slots;
     else bar_sync(barid, nthr);
+    if (!(diag & 16)) {
 #pragma unroll
     for (int q = 0; q < 8; q++) x2[x2_slot(hi, lo, q)] = v[q];
-    bar_sync(barid, nthr);
+    if (diag & 4) __syncwarp(); else bar_sync(barid, nthr);
 #pragma unroll
     for (int q = 0; q < 8; q++) v[q] = x2[x2_slot(lo, q, hi)];
+    }
     {
         cplx w[7];
         tw2.get(w);
         inv_pass(v, w, 1);
     }
     cplx *x1 = xb.x1;
+    if (!(diag & 8)) {
 #pragma unroll
     for (int q = 0; q < 8; q++) x1[x1_slot(hi, lo, q)] = v[q];
     __syncwarp();
 #pragma unroll
     for (int q = 0; q < 8; q++) v[q] = x1[x1_slot(hi, q, lo)];
+    }
     inv_pass1(v);
 }
 
@@ -174,8 +217,12 @@ struct Layout {
     static constexpr int kTw2Mode = kTwShared ? kTwSmem : (KCT > 4 ? kTwPow : kTwFull);   // KCT = 5, 6 without teams: keep r, r^2, r^4
     static constexpr int kTw3Mode = kTwShared ? kTwSmem : (KCT > 5 ? kTwPow : kTwFull);
     static constexpr bool kDbX2 = KCT <= 4;     // double-buffered X2 (fits when only 4 groups share the SM)
+#ifdef TFHE_B200_STAGES
+    static constexpr int kStages = KCT <= 4 ? TFHE_B200_STAGES : 3;   // variant builds: deeper ring where shared memory allows
+#else
     static constexpr int kStages = 3;   // key-ring depth (4 measured no faster; KCT = 2 with a 2-deep ring and two CTAs, i.e. two
                                         // independent rings, per SM: 91.0 k/s, same as one KCT = 4 CTA -- ring coupling is not a limiter)
+#endif
     static constexpr bool kAccTmem = !kTwShared && KCT > 5;   // MAC accumulators in TMEM (measured slower than KCT = 4)
     static constexpr int kTmemCols = 256;       // 64 columns per warp, up to 3 warps per TMEM quadrant
     static constexpr int kAccBytes = 2 * kN * 4;
@@ -190,13 +237,15 @@ struct Layout {
     }
 };
 
-template <int KCT, bool USE_TMA, bool MARGIN, int TEAM = 1, int LT = 0>
+template <int KCT, bool USE_TMA, bool MARGIN, int TEAM = 1, int LT = 0, int TWT = 0>
 __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(const BrArgs P) {
     using Lay = Layout<KCT, TEAM>;
-    constexpr int POW = Lay::kTw2Mode, POW3 = Lay::kTw3Mode;
+    constexpr bool TWT_ON = TWT != 0;              // both twiddle sets in tensor memory, accumulators in registers
+    constexpr int POW = TWT_ON ? kTwTmem : Lay::kTw2Mode, POW3 = TWT_ON ? kTwTmem : Lay::kTw3Mode;
     constexpr bool DBX2 = Lay::kDbX2;
     constexpr int kStages = Lay::kStages;
-    constexpr bool ACCT = Lay::kAccTmem;
+    constexpr bool ACCT = !TWT_ON && Lay::kAccTmem;
+    constexpr bool USE_TMEM = ACCT || TWT_ON;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // ---- carve shared memory
     unsigned char *ptr = smem_raw;
@@ -205,7 +254,8 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(ptr);
     uint64_t *empty_bar = full_bar + kMaxStages;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(ptr + 64);
-    ptr += 80;
+    uint32_t *ring_cnt = reinterpret_cast<uint32_t *>(ptr + 80);   // [kMaxStages] releases per stage, monotone
+    ptr += 96;
     const int n = P.n, L = LT > 0 ? LT : P.L, bgbit = LT == 3 ? 6 : P.bgbit;   // LT = 3: the L = 3 / BGBIT = 6 sets (80/110/128-bit)
     static_assert(TEAM == 1 || (TEAM == 2 && KCT % 2 == 0), "a team never straddles CTAs");
     constexpr int kTeamThreads = TEAM * kGroupThreads;
@@ -217,10 +267,13 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
     const int first_ct = blockIdx.x * KCT;
     const int n_active = min(KCT, (int)P.B - first_ct);
 
+    static_assert(Lay::kStages <= kMaxStages, "ring bookkeeping has room for kMaxStages stages");
+    const uint32_t ring_warps = (uint32_t)(((n_active + TEAM - 1) / TEAM) * TEAM * 2);   // consumer warps of this CTA
     if (USE_TMA && tid == 0) {
         for (int s = 0; s < kStages; s++) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], ((n_active + TEAM - 1) / TEAM) * TEAM * 2);   // one arrival per consumer warp
+            mbar_init(&empty_bar[s], ring_warps);   // one arrival per consumer warp
+            ring_cnt[s] = 0u;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -228,13 +281,13 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
     if (Lay::kTwShared) {
         for (int j = tid; j < kTw2Len + kTw3Len; j += KCT * kGroupThreads) tw_tab[j] = j < kTw2Len ? P.tw2[j] : P.tw3[j - kTw2Len];
     }
-    if (ACCT && tid < 32) {
+    if (USE_TMEM && tid < 32) {
         tmem_alloc(tmem_slot, Lay::kTmemCols);
         tmem_fence_before_sync();
     }
     __syncthreads();
     uint32_t tmem_base = 0;
-    if (ACCT) {
+    if (USE_TMEM) {
         tmem_fence_after_sync();
         tmem_base = *tmem_slot;
     }
@@ -270,7 +323,28 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
     // per-thread twiddles: role B node q2 = lo, role C node t
     Tw2<POW> tw2;
     Tw2<POW3> tw3;
-    if (POW3 == kTwSmem) {
+    if (TWT_ON) {   // park both sets in this warp's tensor-memory window: tw2 in columns [0, 32), tw3 in [32, 64)
+        uint32_t r[32];
+#pragma unroll
+        for (int k = 28; k < 32; k++) r[k] = 0u;
+#pragma unroll
+        for (int p = 1; p < 8; p++) {
+            const cplx w = P.tw2[tw2_index(p, lo)];
+            r[4 * p - 4] = (uint32_t)__double2loint(w.re); r[4 * p - 3] = (uint32_t)__double2hiint(w.re);
+            r[4 * p - 2] = (uint32_t)__double2loint(w.im); r[4 * p - 1] = (uint32_t)__double2hiint(w.im);
+        }
+        tmem_st32(my_tmem, r);
+#pragma unroll
+        for (int p = 1; p < 8; p++) {
+            const cplx w = P.tw3[tw3_index(p, t)];
+            r[4 * p - 4] = (uint32_t)__double2loint(w.re); r[4 * p - 3] = (uint32_t)__double2hiint(w.re);
+            r[4 * p - 2] = (uint32_t)__double2loint(w.im); r[4 * p - 1] = (uint32_t)__double2hiint(w.im);
+        }
+        tmem_st32(my_tmem + 32u, r);
+        tmem_wait_st();
+        tw2.taddr = my_tmem;
+        tw3.taddr = my_tmem + 32u;
+    } else if (POW3 == kTwSmem) {
         tw3.tab = tw_tab + kTw2Len + tw3_index(1, t); tw3.stride = 64;
     } else if (POW3 == kTwPow) {
         tw3.w[0] = P.tw3[tw3_index(1, t)]; tw3.w[1] = P.tw3[tw3_index(2, t)]; tw3.w[2] = P.tw3[tw3_index(4, t)];
@@ -278,7 +352,8 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
 #pragma unroll
         for (int p = 1; p < 8; p++) tw3.w[p - 1] = P.tw3[tw3_index(p, t)];
     }
-    if (POW == kTwSmem) {
+    if (TWT_ON) {
+    } else if (POW == kTwSmem) {
         tw2.tab = tw_tab + tw2_index(1, lo); tw2.stride = 8;
     } else if (POW == kTwPow) {
         tw2.w[0] = P.tw2[tw2_index(1, lo)]; tw2.w[1] = P.tw2[tw2_index(2, lo)]; tw2.w[2] = P.tw2[tw2_index(4, lo)];
@@ -320,13 +395,31 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
     uint32_t phase = 0;
     double margin = 0.0;
     Producer pr;
-    pr.src = P.bsk; pr.ring = bsk_ring; pr.full_bar = full_bar; pr.empty_bar = empty_bar;
-    pr.remaining = USE_TMA ? n * 2 * L : 0; pr.issued = 0; pr.stage = 0; pr.phase = 0; pr.stages = kStages;
-    pr.active = USE_TMA && tid == 0;
-    pr.policy = pr.active ? l2_policy_evict_last() : 0;
-    if (USE_TMA) {   // fill the ring
+    pr.ring = bsk_ring; pr.full_bar = full_bar; pr.empty_bar = empty_bar; pr.stages = kStages;
+    pr.ring_cnt = ring_cnt; pr.bsk = P.bsk; pr.total = (uint32_t)(n * 2 * L); pr.ring_warps = ring_warps;
+#ifdef TFHE_B200_DIAG
+    const int diag = P.diag;
+#else
+    constexpr int diag = 0;
+#endif
+    if (kRingLastArriver) {
+        pr.active = false; pr.remaining = 0;
+        if (USE_TMA && tid == 0 && !DIAG_ON(P, 0)) {   // fill the ring; every later bulk copy is issued by the consumers (ring_check)
+            const uint64_t policy = l2_policy_evict_last();
+            for (int s = 0; s < kStages && s < n * 2 * L; s++) {
+                mbar_arrive_expect_tx(&full_bar[s], kBskChunkBytes);
+                bulk_g2s(bsk_ring + s * kBskChunkCplx, P.bsk + (size_t)s * kBskChunkCplx, kBskChunkBytes, &full_bar[s], policy);
+            }
+        }
+    } else {
+        pr.src = P.bsk;
+        pr.remaining = (USE_TMA && !DIAG_ON(P, 0)) ? n * 2 * L : 0; pr.issued = 0; pr.stage = 0; pr.phase = 0;
+        pr.active = USE_TMA && tid == 0;
+        pr.policy = pr.active ? l2_policy_evict_last() : 0;
+        if (USE_TMA) {   // fill the ring
 #pragma unroll
-        for (int s = 0; s < kStages; s++) producer_poll(pr);
+            for (int s = 0; s < kStages; s++) producer_poll(pr);
+        }
     }
 
     // CTAs of one wave start in lock step and would ask L2 for the same 16 KiB key chunk in the same few hundred cycles for
@@ -350,29 +443,44 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
                 for (int l = 0; l < L; l++) {
                     cplx v[8];
                     digits_to_cplx(v, d, 32 - (l + 1) * bgbit, mask, half_bg);
-                    fwd_transform<USE_TMA, DBX2, POW, POW3>(v, xb, tw2, tw3, hi, lo, barid, pr, kTeamThreads);
+                    fwd_transform<USE_TMA, DBX2, POW, POW3>(v, xb, tw2, tw3, hi, lo, barid, pr, kTeamThreads, diag);
                     const cplx *chunk;
                     if (USE_TMA) {
-                        while (!mbar_try_wait(&full_bar[stage], phase)) producer_poll(pr);
+                        if (!DIAG_ON(P, 0) && !DIAG_ON(P, 5)) {
+                            if (kRingLastArriver) mbar_wait(&full_bar[stage], phase);
+                            else
+                                while (!mbar_try_wait(&full_bar[stage], phase)) producer_poll(pr);
+                        }
                         chunk = bsk_ring + stage * kBskChunkCplx;
                     } else {
                         chunk = P.bsk + ((size_t)i * 2 * L + h * L + l) * kBskChunkCplx;
                     }
+                    if (DIAG_ON(P, 1)) {
+#pragma unroll
+                        for (int q = 0; q < 8; q++) {
+                            cmac(oa[q], v[q], cplx{1.0, 0.5});
+                            cmac(ob[q], v[q], cplx{0.25, 1.0});
+                        }
+                    } else {
 #pragma unroll
                     for (int q = 0; q < 8; q++) {
                         cmac(oa[q], v[q], chunk[bsk_slot(0, q, t)]);
                         cmac(ob[q], v[q], chunk[bsk_slot(1, q, t)]);
                     }
-                    if (USE_TMA) {
-                        __syncwarp();
-                        if ((tid & 31) == 0) mbar_arrive(&empty_bar[stage]);
+                    }
+                    if (USE_TMA && !DIAG_ON(P, 0)) {
+                        if (kRingLastArriver) ring_release(pr, stage, (uint32_t)((i * 2 + h) * L + l), tid & 31);
+                        else {
+                            __syncwarp();
+                            if ((tid & 31) == 0) mbar_arrive(&empty_bar[stage]);
+                        }
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
-            inv_transform<USE_TMA, DBX2, POW, POW3>(oa, xb, tw2, tw3, hi, lo, barid, pr, kTeamThreads);
+            inv_transform<USE_TMA, DBX2, POW, POW3>(oa, xb, tw2, tw3, hi, lo, barid, pr, kTeamThreads, diag);
             round_accumulate<MARGIN>(oa, acc_a, t, wide, margin);
-            inv_transform<USE_TMA, DBX2, POW, POW3>(ob, xb, tw2, tw3, hi, lo, barid, pr, kTeamThreads);
+            inv_transform<USE_TMA, DBX2, POW, POW3>(ob, xb, tw2, tw3, hi, lo, barid, pr, kTeamThreads, diag);
             round_accumulate<MARGIN>(ob, acc_b, t, wide, margin);
         } else {
             // ---- accumulators in TMEM (168-register budget): each half is loaded, updated and stored back
@@ -388,7 +496,9 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
                     fwd_transform<USE_TMA, DBX2, POW, POW3>(v, xb, tw2, tw3, hi, lo, barid, pr, kTeamThreads);
                     const cplx *chunk;
                     if (USE_TMA) {
-                        while (!mbar_try_wait(&full_bar[stage], phase)) producer_poll(pr);
+                        if (kRingLastArriver) mbar_wait(&full_bar[stage], phase);
+                        else
+                            while (!mbar_try_wait(&full_bar[stage], phase)) producer_poll(pr);
                         chunk = bsk_ring + stage * kBskChunkCplx;
                     } else {
                         chunk = P.bsk + ((size_t)i * 2 * L + h * L + l) * kBskChunkCplx;
@@ -408,8 +518,11 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
                         tmem_store_cplx8(my_tmem + 32 * ab, o);
                     }
                     if (USE_TMA) {
-                        __syncwarp();
-                        if ((tid & 31) == 0) mbar_arrive(&empty_bar[stage]);
+                        if (kRingLastArriver) ring_release(pr, stage, (uint32_t)((i * 2 + h) * L + l), tid & 31);
+                        else {
+                            __syncwarp();
+                            if ((tid & 31) == 0) mbar_arrive(&empty_bar[stage]);
+                        }
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -440,8 +553,8 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
         for (int s = 16; s > 0; s >>= 1) margin = fmax(margin, __shfl_xor_sync(0xffffffffu, margin, s));
         if ((tid & 31) == 0) atomicMax(P.margin_bits, (unsigned long long)__double_as_longlong(margin));
     }
-    if (ACCT) {
-        tmem_wait_st();
+    if (USE_TMEM) {
+        if (ACCT) tmem_wait_st();
         tmem_fence_before_sync();
         bar_sync(15, ((n_active + TEAM - 1) / TEAM) * kTeamThreads);      // every active warp is done with its TMEM window
         if (tid < 32) {
@@ -803,11 +916,24 @@ cudaError_t launch_latency(const BrArgs &a, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+// tensor-memory twiddles (tuning key "twt"): throughput kernel at KCT = 4, 5, 6, TMA ring, no margin tracking
+template <int KCT>
+cudaError_t launch_twt(const BrArgs &a, cudaStream_t s) {
+    using Lay = Layout<KCT, 1>;
+    const size_t smem = Lay::kStages * kBskChunkBytes + 96 + (size_t)KCT * Lay::group_bytes(a.n);
+    auto kern = blind_rotate_kernel<KCT, true, false, 1, 0, 1>;
+    if (a.L == 3 && a.bgbit == 6 && !a.wide_round) kern = blind_rotate_kernel<KCT, true, false, 1, 3, 1>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<(a.B + KCT - 1) / KCT, KCT * kGroupThreads, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
 template <int KCT, bool USE_TMA, bool MARGIN, int TEAM = 1>
 cudaError_t launch_variant(const BrArgs &a, cudaStream_t s) {
     using Lay = Layout<KCT, TEAM>;
     const int threads = KCT * kGroupThreads;
-    const size_t smem = (USE_TMA ? Lay::kStages * kBskChunkBytes : 0) + 80 + Lay::kTwBytes + (size_t)KCT * Lay::group_bytes(a.n);
+    const size_t smem = (USE_TMA ? Lay::kStages * kBskChunkBytes : 0) + 96 + Lay::kTwBytes + (size_t)KCT * Lay::group_bytes(a.n);
     auto kern = blind_rotate_kernel<KCT, USE_TMA, MARGIN, TEAM>;
     // the L = 3 / BGBIT = 6 sets (80/110/128-bit) get their own instantiation: digit loop unrolled, shifts, masks and the
     // rounding mode compile-time (+5 % on the 128-bit bench; profiles/r01_wave_scaling.log)
@@ -854,46 +980,52 @@ cudaError_t launch_blind_rotate(const BrArgs &a, const BrTuning &tune, bool trac
             default: return track_margin ? launch_latency<3, true>(a, s) : launch_latency<3, false>(a, s);
         }
     }
+    // CTA widths and the time one CTA of that width takes, measured on B200 at n = 700 (profiles/r01_wave_scaling.log,
+    // profiles/r02_k1_ring.log): 1 or 2 ciphertexts 4.6 ms, 3: 5.8 ms, 4: 6.15 ms (96.3 k bootstraps/s), 6 with the twiddles in
+    // tensor memory: 8.8 ms (100.8 k/s) -- the densest configuration wherever it is available.
+    const bool twt_ok = tune.twt >= 0 && tune.use_tma != 0 && !track_margin && tune.team != 2;
+    static const int widths[5] = {1, 2, 3, 4, 6};
+    static const double t_cta[5] = {4.6, 4.6, 5.8, 6.15, 8.8};
+    const int n_widths = twt_ok ? 5 : 4;
+    const int dense = widths[n_widths - 1];
+    const double t_dense = t_cta[n_widths - 1];
     int kct = tune.kct;
-    if (kct <= 0 && tune.concurrent != 0) kct = 4;   // densest CTA (ciphertexts per SM-second); idle SMs go to the other lanes
+    if (kct <= 0 && tune.concurrent != 0) kct = dense;   // densest CTA (ciphertexts per SM-second); idle SMs go to the other lanes
     if (kct <= 0 && tune.use_tma != 0 && a.ct_base == 0) {
-        // Mid-size batches: whole waves of the densest CTA (KCT = 4), then the remainder as its own launch with whatever
-        // width is cheapest for it -- e.g. 2,048 ciphertexts = 3 waves x 6.5 ms + 272 ciphertexts at KCT = 2 (4.5 ms)
-        // instead of 4 waves (26 ms).  Ciphertext indices stay global (BrArgs.ct_base), so no pointer is offset.
-        const unsigned wave = sm_total * 4;
+        // Mid-size batches: whole waves of the densest CTA, then the remainder as its own launch with whatever width is
+        // cheapest for it -- e.g. 2,048 ciphertexts = 2 waves of 888 + 272 ciphertexts at KCT = 2 (4.6 ms) instead of a third
+        // 8.8 ms wave.  Ciphertext indices stay global (BrArgs.ct_base), so no pointer is offset.
+        const unsigned wave = sm_total * dense;
         const unsigned full = (a.B / wave) * wave, tail = a.B - full;
         if (full > 0 && tail > 0) {
-            static const double t_cta[5] = {0.0, 4.6, 4.6, 5.8, 6.15};
             double best_tail = 1e30;
-            for (int k = 1; k <= 4; k++) best_tail = std::min(best_tail, ((tail + sm_total * k - 1) / (sm_total * k)) * t_cta[k]);
+            for (int w = 0; w < n_widths; w++) best_tail = std::min(best_tail, ((tail + sm_total * widths[w] - 1) / (sm_total * widths[w])) * t_cta[w]);
             if (tune.latency_mode != 0 && tail <= sm_total && !a.wide_round) best_tail = std::min(best_tail, 2.5);
-            if (best_tail < t_cta[4] - 1e-9) {
+            if (best_tail < t_dense - 1e-9) {
                 BrArgs m = a, r = a;
                 m.B = full;
                 r.B = tail;
                 r.ct_base = full;
                 BrTuning tm = tune;
-                tm.kct = 4;
+                tm.kct = dense;
                 cudaError_t e = launch_blind_rotate(m, tm, track_margin, s, launches);
                 if (e != cudaSuccess) return e;
                 return launch_blind_rotate(r, tune, track_margin, s, launches);
             }
         }
     }
-    if (kct <= 0) {
-        // minimise (number of CTA waves) x (time of one CTA at that width); CTA times measured on B200 at n = 700
-        // (profiles/r01_first_light*.log, profiles/r01_wave_scaling.log): 1 or 2 ciphertexts 4.6 ms, 3: 5.8 ms, 4: 6.15 ms.
-        // (6 with teams of two and shared-memory twiddles: 10.6 ms -- 84 k/s against 91 k/s at 4, so never chosen.)
-        static const double t_cta[5] = {0.0, 4.6, 4.6, 5.8, 6.15};
-        const unsigned sms = tune.sm_count > 0 ? (unsigned)tune.sm_count : 148u;
+    if (kct <= 0) {   // minimise (number of CTA waves) x (time of one CTA at that width)
         double best = 1e30;
-        for (int k = 1; k <= 4; k++) {
-            const unsigned waves = (a.B + sms * k - 1) / (sms * k);
-            const double cost = waves * t_cta[k];
-            if (cost < best - 1e-9) { best = cost; kct = k; }
+        for (int w = 0; w < n_widths; w++) {
+            const unsigned waves = (a.B + sm_total * widths[w] - 1) / (sm_total * widths[w]);
+            const double cost = waves * t_cta[w];
+            if (cost < best - 1e-9) { best = cost; kct = widths[w]; }
         }
     }
     if (launches) (*launches)++;
+    // tensor-memory twiddles: the KCT = 6 default, or forced (tuning key "twt" = 1) at 4 and 5
+    if (twt_ok && (kct == 6 || (tune.twt > 0 && kct >= 4)))
+        return kct == 4 ? launch_twt<4>(a, s) : kct == 5 ? launch_twt<5>(a, s) : launch_twt<6>(a, s);
     if (tune.use_tma != 0 && (kct == 2 || kct == 4 || kct == 6) && tune.team == 2)
         return kct == 2 ? launch_team2<2>(a, track_margin, s) : kct == 4 ? launch_team2<4>(a, track_margin, s) : launch_team2<6>(a, track_margin, s);
     switch (kct) {

@@ -171,6 +171,9 @@ int run_device(tfhe_b200_ctx *c, Device &d, int op, const int32_t *d_ops, const 
     A.margin_bits = c->track_margin ? d.margin_bits : nullptr;
     A.B = (uint32_t)B; A.n = c->prm.n; A.L = c->prm.L; A.bgbit = c->prm.bgbit;
     A.offset = c->offset; A.wide_round = wide_round(c->prm) ? 1 : 0;
+#ifdef TFHE_B200_DIAG
+    A.diag = c->tune.diag;
+#endif
     d.ev_valid = false;
     if (c->timing) CU(c, cudaEventRecord(d.ev[0], d.stream));
     if (c->mode == TFHE_B200_MODE_EXACT) {
@@ -1031,6 +1034,8 @@ int tfhe_b200_set_tuning(tfhe_b200_ctx *c, const char *key, int value) {
     else if (!strcmp(key, "use_tma")) c->tune.use_tma = value;
     else if (!strcmp(key, "latency_mode")) c->tune.latency_mode = value;
     else if (!strcmp(key, "team")) c->tune.team = value;
+    else if (!strcmp(key, "twt")) c->tune.twt = value;
+    else if (!strcmp(key, "diag")) c->tune.diag = value;
     else if (!strcmp(key, "timing")) c->timing = value != 0;
     else if (!strcmp(key, "ks_tile")) c->ks_tile = value;
     else if (!strcmp(key, "ks_vec")) c->ks_vec = value;

@@ -31,6 +31,9 @@ struct BrArgs {
     int n, L, bgbit;
     uint32_t offset;        // CloudKey.decomposition_offset
     int wide_round;         // 1: F2I.S64 rounding (large-digit sets), 0: magic-add rounding
+#ifdef TFHE_B200_DIAG
+    int diag;               // diagnostic builds only (blind_rotate.cu): parts of the kernel switched off
+#endif
 };
 
 struct BrTuning {
@@ -41,6 +44,8 @@ struct BrTuning {
                             // sm_count / 2: one two-CTA cluster per ciphertext (2: never the cluster kernel, 0: throughput kernel only)
     int concurrent = 0; // 1: other kernels share the GPU (circuit lanes): pick the CTA width by work per SM-second, not by waves
     int team = 0;       // ciphertexts sharing a warp in adjacent lanes (0 = default, 1, 2)
+    int twt = 0;        // pass-2 / pass-3 twiddles in tensor memory: 0 = where it wins (six ciphertexts per CTA), 1 = also at 4 and 5, -1 = never
+    int diag = 0;       // diagnostic builds only
 };
 
 // returns cudaSuccess or the launch error; *launches += kernels launched

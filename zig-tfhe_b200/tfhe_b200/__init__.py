@@ -25,7 +25,8 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libtfhe_b200.so")
+# TFHE_B200_LIB: another build of the same library (tools/build_diag.sh makes a diagnostic one); never a different implementation
+LIB_PATH = os.environ.get("TFHE_B200_LIB") or os.path.join(os.path.dirname(_HERE), "libtfhe_b200.so")
 
 NAND, OR, AND, XOR, XNOR, NOR, ANDNY, ANDYN, ORNY, ORYN = range(10)
 GATE_NAMES = ["nand", "or", "and", "xor", "xnor", "nor", "andny", "andyn", "orny", "oryn"]
