@@ -100,17 +100,19 @@ struct Tw2 {
 };
 
 // forward transform, role A registers in -> role C (leaf order) out
-template <bool USE_TMA, bool DBX2, int POW, int POW3>
+// ALIAS: X1 lives in the X2 buffer this transform does NOT use for its own X2 exchange (rows of this warp only), see
+// Layout::kX1Alias for why that is race-free.
+template <bool USE_TMA, bool DBX2, int POW, int POW3, bool ALIAS = false>
 __device__ __forceinline__ void fwd_transform(cplx (&v)[8], Xbuf &xb, const Tw2<POW> &tw2, const Tw2<POW3> &tw3, int hi, int lo,
                                               int barid, Producer &pr, int nthr = kGroupThreads, int diag = 0) {
     fwd_pass1(v);
-    cplx *x1 = xb.x1;
+    cplx *x1 = ALIAS ? xb.x2 + (xb.flip ^ kX2Slots) : xb.x1;
     if (!(diag & 8)) {
 #pragma unroll
-    for (int q = 0; q < 8; q++) x1[x1_slot(hi, q, lo)] = v[q];
+    for (int q = 0; q < 8; q++) x1[ALIAS ? x1a_slot(hi, q, lo) : x1_slot(hi, q, lo)] = v[q];
     __syncwarp();
 #pragma unroll
-    for (int q = 0; q < 8; q++) v[q] = x1[x1_slot(hi, lo, q)];
+    for (int q = 0; q < 8; q++) v[q] = x1[ALIAS ? x1a_slot(hi, lo, q) : x1_slot(hi, lo, q)];
     }
     {
         cplx w[7];
@@ -136,7 +138,7 @@ __device__ __forceinline__ void fwd_transform(cplx (&v)[8], Xbuf &xb, const Tw2<
 }
 
 // inverse transform, role C (leaf order) in -> role A out: v[p] = c_e, e = 64 p + 8 lo + hi
-template <bool USE_TMA, bool DBX2, int POW, int POW3>
+template <bool USE_TMA, bool DBX2, int POW, int POW3, bool ALIAS = false>
 __device__ __forceinline__ void inv_transform(cplx (&v)[8], Xbuf &xb, const Tw2<POW> &tw2, const Tw2<POW3> &tw3, int hi, int lo,
                                               int barid, Producer &pr, int nthr = kGroupThreads, int diag = 0) {
     {
@@ -160,13 +162,16 @@ __device__ __forceinline__ void inv_transform(cplx (&v)[8], Xbuf &xb, const Tw2<
         tw2.get(w);
         inv_pass(v, w, 1);
     }
-    cplx *x1 = xb.x1;
+    // ALIAS: the inverse X2 reads cross both warps' rows, so X1 may reuse that same buffer (this warp's rows) only once
+    // every thread of the group has finished them: one more group barrier, on two of the eight transforms of a step
+    cplx *x1 = ALIAS ? x2 : xb.x1;
+    if (ALIAS) bar_sync(barid, nthr);
     if (!(diag & 8)) {
 #pragma unroll
-    for (int q = 0; q < 8; q++) x1[x1_slot(hi, lo, q)] = v[q];
+    for (int q = 0; q < 8; q++) x1[ALIAS ? x1a_slot(hi, lo, q) : x1_slot(hi, lo, q)] = v[q];
     __syncwarp();
 #pragma unroll
-    for (int q = 0; q < 8; q++) v[q] = x1[x1_slot(hi, q, lo)];
+    for (int q = 0; q < 8; q++) v[q] = x1[ALIAS ? x1a_slot(hi, q, lo) : x1_slot(hi, q, lo)];
     }
     inv_pass1(v);
 }
@@ -210,13 +215,20 @@ __device__ __forceinline__ void round_accumulate(const cplx (&v)[8], uint32_t *a
 }
 
 // shared-memory footprint of one ciphertext group
-template <int KCT, int TEAM = 1>
+template <int KCT, int TEAM = 1, bool ALIAS = false>
 struct Layout {
+    // ALIAS (six ciphertexts per CTA with tensor-memory twiddles): X1 has no buffer of its own.  In a forward transform it
+    // uses this warp's rows of the X2 buffer of the PREVIOUS transform: those rows are read by this warp alone (forward X2
+    // reads are partitioned by warp), the other warp writes that buffer again only one transform later, after the group
+    // barrier this warp reaches with X1 long finished, and a forward transform never directly follows an inverse one without
+    // the end-of-step barrier in between.  In an inverse transform X1 follows X2 and reuses the same buffer after an extra
+    // barrier.  The 9 KiB per ciphertext this frees pay for a double-buffered X2: 10 group barriers per step instead of 16.
+    static constexpr bool kX1Alias = ALIAS;
     // teams of two at KCT > 4 (168-register budget): both twiddle tables live in shared memory
     static constexpr bool kTwShared = TEAM == 2 && KCT > 4;
     static constexpr int kTw2Mode = kTwShared ? kTwSmem : (KCT > 4 ? kTwPow : kTwFull);   // KCT = 5, 6 without teams: keep r, r^2, r^4
     static constexpr int kTw3Mode = kTwShared ? kTwSmem : (KCT > 5 ? kTwPow : kTwFull);
-    static constexpr bool kDbX2 = KCT <= 4;     // double-buffered X2 (fits when only 4 groups share the SM)
+    static constexpr bool kDbX2 = KCT <= 4 || ALIAS;     // double-buffered X2 (fits when only 4 groups share the SM, or without X1 buffers)
 #ifdef TFHE_B200_STAGES
     static constexpr int kStages = KCT <= 4 ? TFHE_B200_STAGES : 3;   // variant builds: deeper ring where shared memory allows
 #else
@@ -226,7 +238,7 @@ struct Layout {
     static constexpr bool kAccTmem = !kTwShared && KCT > 5;   // MAC accumulators in TMEM (measured slower than KCT = 4)
     static constexpr int kTmemCols = 256;       // 64 columns per warp, up to 3 warps per TMEM quadrant
     static constexpr int kAccBytes = 2 * kN * 4;
-    static constexpr int kX1Bytes = kX1Slots * 16;
+    static constexpr int kX1Bytes = ALIAS ? 0 : kX1Slots * 16;
     static constexpr int kX2Bytes = kX2Slots * 16;
     static constexpr int kTwBytes = kTwShared ? (kTw2Len + kTw3Len) * 16 : 0;
     __host__ __device__ static constexpr int group_bytes(int n) {
@@ -239,7 +251,8 @@ struct Layout {
 
 template <int KCT, bool USE_TMA, bool MARGIN, int TEAM = 1, int LT = 0, int TWT = 0>
 __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(const BrArgs P) {
-    using Lay = Layout<KCT, TEAM>;
+    using Lay = Layout<KCT, TEAM, (TWT != 0 && KCT > 4)>;
+    constexpr bool XA = Lay::kX1Alias;
     constexpr bool TWT_ON = TWT != 0;              // both twiddle sets in tensor memory, accumulators in registers
     constexpr int POW = TWT_ON ? kTwTmem : Lay::kTw2Mode, POW3 = TWT_ON ? kTwTmem : Lay::kTw3Mode;
     constexpr bool DBX2 = Lay::kDbX2;
@@ -443,7 +456,7 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
                 for (int l = 0; l < L; l++) {
                     cplx v[8];
                     digits_to_cplx(v, d, 32 - (l + 1) * bgbit, mask, half_bg);
-                    fwd_transform<USE_TMA, DBX2, POW, POW3>(v, xb, tw2, tw3, hi, lo, barid, pr, kTeamThreads, diag);
+                    fwd_transform<USE_TMA, DBX2, POW, POW3, XA>(v, xb, tw2, tw3, hi, lo, barid, pr, kTeamThreads, diag);
                     const cplx *chunk;
                     if (USE_TMA) {
                         if (!DIAG_ON(P, 0) && !DIAG_ON(P, 5)) {
@@ -478,9 +491,9 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
                     }
                 }
             }
-            inv_transform<USE_TMA, DBX2, POW, POW3>(oa, xb, tw2, tw3, hi, lo, barid, pr, kTeamThreads, diag);
+            inv_transform<USE_TMA, DBX2, POW, POW3, XA>(oa, xb, tw2, tw3, hi, lo, barid, pr, kTeamThreads, diag);
             round_accumulate<MARGIN>(oa, acc_a, t, wide, margin);
-            inv_transform<USE_TMA, DBX2, POW, POW3>(ob, xb, tw2, tw3, hi, lo, barid, pr, kTeamThreads, diag);
+            inv_transform<USE_TMA, DBX2, POW, POW3, XA>(ob, xb, tw2, tw3, hi, lo, barid, pr, kTeamThreads, diag);
             round_accumulate<MARGIN>(ob, acc_b, t, wide, margin);
         } else {
             // ---- accumulators in TMEM (168-register budget): each half is loaded, updated and stored back
@@ -919,7 +932,7 @@ cudaError_t launch_latency(const BrArgs &a, cudaStream_t s) {
 // tensor-memory twiddles (tuning key "twt"): throughput kernel at KCT = 4, 5, 6, TMA ring, no margin tracking
 template <int KCT>
 cudaError_t launch_twt(const BrArgs &a, cudaStream_t s) {
-    using Lay = Layout<KCT, 1>;
+    using Lay = Layout<KCT, 1, (KCT > 4)>;
     const size_t smem = Lay::kStages * kBskChunkBytes + 96 + (size_t)KCT * Lay::group_bytes(a.n);
     auto kern = blind_rotate_kernel<KCT, true, false, 1, 0, 1>;
     if (a.L == 3 && a.bgbit == 6 && !a.wide_round) kern = blind_rotate_kernel<KCT, true, false, 1, 3, 1>;
@@ -982,10 +995,10 @@ cudaError_t launch_blind_rotate(const BrArgs &a, const BrTuning &tune, bool trac
     }
     // CTA widths and the time one CTA of that width takes, measured on B200 at n = 700 (profiles/r01_wave_scaling.log,
     // profiles/r02_k1_ring.log): 1 or 2 ciphertexts 4.6 ms, 3: 5.8 ms, 4: 6.15 ms (96.3 k bootstraps/s), 6 with the twiddles in
-    // tensor memory: 8.8 ms (100.8 k/s) -- the densest configuration wherever it is available.
+    // tensor memory and X1 laid over the spare X2 buffer: 8.62 ms (103.1 k/s) -- the densest configuration wherever it is available.
     const bool twt_ok = tune.twt >= 0 && tune.use_tma != 0 && !track_margin && tune.team != 2;
     static const int widths[5] = {1, 2, 3, 4, 6};
-    static const double t_cta[5] = {4.6, 4.6, 5.8, 6.15, 8.8};
+    static const double t_cta[5] = {4.6, 4.6, 5.8, 6.15, 8.62};
     const int n_widths = twt_ok ? 5 : 4;
     const int dense = widths[n_widths - 1];
     const double t_dense = t_cta[n_widths - 1];
@@ -994,7 +1007,7 @@ cudaError_t launch_blind_rotate(const BrArgs &a, const BrTuning &tune, bool trac
     if (kct <= 0 && tune.use_tma != 0 && a.ct_base == 0) {
         // Mid-size batches: whole waves of the densest CTA, then the remainder as its own launch with whatever width is
         // cheapest for it -- e.g. 2,048 ciphertexts = 2 waves of 888 + 272 ciphertexts at KCT = 2 (4.6 ms) instead of a third
-        // 8.8 ms wave.  Ciphertext indices stay global (BrArgs.ct_base), so no pointer is offset.
+        // 8.6 ms wave.  Ciphertext indices stay global (BrArgs.ct_base), so no pointer is offset.
         const unsigned wave = sm_total * dense;
         const unsigned full = (a.B / wave) * wave, tail = a.B - full;
         if (full > 0 && tail > 0) {

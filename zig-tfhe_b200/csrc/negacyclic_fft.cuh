@@ -192,6 +192,9 @@ TFHE_HD int x1_slot(int k0, int q2, int k1) { return k0 * 72 + q2 * 9 + k1; }
 // (stride 73 = 1 mod 8); reads: lanes differ in q1 (stride 9).
 constexpr int kX2Slots = 7 * 73 + 7 * 9 + 8;
 TFHE_HD int x2_slot(int q2, int q1, int k0) { return q2 * 73 + q1 * 9 + k0; }
+// X1 laid over an X2 buffer (row pitch 73 like X2's, so that the rows a warp uses for X1 are exactly the rows it alone reads
+// in the forward X2 exchange): six ciphertexts per CTA then afford a double-buffered X2 (blind_rotate.cu, Layout::kX1Alias)
+TFHE_HD int x1a_slot(int k0, int q2, int k1) { return k0 * 73 + q2 * 9 + k1; }
 
 // ---- accumulator layout in shared memory ----
 // Coefficient e of a polynomial lives at acc_pos(e): the two low 3-bit fields of e are swapped, so the
