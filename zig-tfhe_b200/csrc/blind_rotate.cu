@@ -225,7 +225,7 @@ struct Layout {
     // barrier.  The 9 KiB per ciphertext this frees pay for a double-buffered X2: 10 group barriers per step instead of 16.
     static constexpr bool kX1Alias = ALIAS;
     // teams of two at KCT > 4 (168-register budget): both twiddle tables live in shared memory
-    static constexpr bool kTwShared = TEAM == 2 && KCT > 4;
+    static constexpr bool kTwShared = TEAM == 2 && KCT > 4 && !ALIAS;
     static constexpr int kTw2Mode = kTwShared ? kTwSmem : (KCT > 4 ? kTwPow : kTwFull);   // KCT = 5, 6 without teams: keep r, r^2, r^4
     static constexpr int kTw3Mode = kTwShared ? kTwSmem : (KCT > 5 ? kTwPow : kTwFull);
     static constexpr bool kDbX2 = KCT <= 4 || ALIAS;     // double-buffered X2 (fits when only 4 groups share the SM, or without X1 buffers)
@@ -252,6 +252,7 @@ struct Layout {
 template <int KCT, bool USE_TMA, bool MARGIN, int TEAM = 1, int LT = 0, int TWT = 0>
 __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(const BrArgs P) {
     using Lay = Layout<KCT, TEAM, (TWT != 0 && KCT > 4)>;
+    static_assert(TWT == 0 || TEAM == 1 || KCT > 4, "teams of two with tensor-memory twiddles: six ciphertexts per CTA only");
     constexpr bool XA = Lay::kX1Alias;
     constexpr bool TWT_ON = TWT != 0;              // both twiddle sets in tensor memory, accumulators in registers
     constexpr int POW = TWT_ON ? kTwTmem : Lay::kTw2Mode, POW3 = TWT_ON ? kTwTmem : Lay::kTw3Mode;
@@ -930,12 +931,12 @@ cudaError_t launch_latency(const BrArgs &a, cudaStream_t s) {
 }
 
 // tensor-memory twiddles (tuning key "twt"): throughput kernel at KCT = 4, 5, 6, TMA ring, no margin tracking
-template <int KCT>
+template <int KCT, int TEAM = 1>
 cudaError_t launch_twt(const BrArgs &a, cudaStream_t s) {
-    using Lay = Layout<KCT, 1, (KCT > 4)>;
+    using Lay = Layout<KCT, TEAM, (KCT > 4)>;
     const size_t smem = Lay::kStages * kBskChunkBytes + 96 + (size_t)KCT * Lay::group_bytes(a.n);
-    auto kern = blind_rotate_kernel<KCT, true, false, 1, 0, 1>;
-    if (a.L == 3 && a.bgbit == 6 && !a.wide_round) kern = blind_rotate_kernel<KCT, true, false, 1, 3, 1>;
+    auto kern = blind_rotate_kernel<KCT, true, false, TEAM, 0, 1>;
+    if (a.L == 3 && a.bgbit == 6 && !a.wide_round) kern = blind_rotate_kernel<KCT, true, false, TEAM, 3, 1>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<(a.B + KCT - 1) / KCT, KCT * kGroupThreads, smem, s>>>(a);
@@ -1037,6 +1038,8 @@ cudaError_t launch_blind_rotate(const BrArgs &a, const BrTuning &tune, bool trac
     }
     if (launches) (*launches)++;
     // tensor-memory twiddles: the KCT = 6 default, or forced (tuning key "twt" = 1) at 4 and 5
+    // (teams of two on top of it -- launch_twt<6, 2>, key loads of two ciphertexts merged -- measured 102.7 k against 103.3 k/s:
+    // not instantiated)
     if (twt_ok && (kct == 6 || (tune.twt > 0 && kct >= 4)))
         return kct == 4 ? launch_twt<4>(a, s) : kct == 5 ? launch_twt<5>(a, s) : launch_twt<6>(a, s);
     if (tune.use_tma != 0 && (kct == 2 || kct == 4 || kct == 6) && tune.team == 2)
