@@ -42,6 +42,8 @@ struct Device {
     cplx *exact_shared = nullptr;     // make_exact_shared_tables(): twist[512] in acc_pos order + 7 pass-A twiddles
     unsigned long long *margin_bits = nullptr;
     Buf a, b, out, lv1, ops, tv, trlwe, lut, ksdig;
+    void *stage[2] = {nullptr, nullptr};            // host_copy: pinned staging buffers (allocated on first use)
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // K1 start, K1 end / K2 start, K2 end (timing mode)
     bool ev_valid = false;
     uint64_t launches = 0;             // kernels launched on this device by its host thread (summed by tfhe_b200_launch_count)
@@ -65,6 +67,8 @@ struct tfhe_b200_ctx {
     uint64_t launches = 0;
     bool timing = false;
     int ks_tile = 0, ks_vec = 0, ks_fill = 0, ks_rot = 0;   // key-switch tuning overrides (0 = automatic)
+    int host_copy_threads = 8;            // large copies from / to PAGEABLE caller memory are staged through pinned buffers by this many
+                                          // memcpy threads (0 = plain cudaMemcpyAsync from the caller's buffer)
     int ks_tc = 0;                        // tensor-core key switch: 0 = automatic (batches >= ks_tc_min), 1 = always, -1 = never
     int ks_tc_min = 192;
     size_t max_chunk = (size_t)1 << 18;   // ciphertexts per device per launch
@@ -199,6 +203,74 @@ int run_device(tfhe_b200_ctx *c, Device &d, int op, const int32_t *d_ops, const 
 
 enum class Out { LV0, LV0_NOKS, LV1, TRLWE };
 
+// One copy between a caller buffer and device memory, ordered on d.stream like a cudaMemcpyAsync there.
+// Pageable host memory (what Zig's page_allocator hands out) goes through the driver's own staging at ~12 GB/s, blocks the
+// issuing thread, and the driver serialises such copies even when several threads issue them on several streams (measured,
+// profiles/r02_host_path.log: 1, 2, 4, 8 threads all give 96.0-96.4 k gates/s end to end against 101.2 k from pinned
+// memory).  Page-locking the caller's buffers for the duration of the call is worse still: cudaHostRegister of the 552 MB
+// of a 65,536-gate call costs ~390 ms (63.5 k gates/s).  So large pageable copies are staged here: `host_copy_threads`
+// host threads memcpy 32 MiB pieces between the caller's buffer and two pinned staging buffers while the DMA engine
+// moves the previous piece.  Pinned or registered caller memory keeps the single asynchronous copy.
+constexpr size_t kStagePiece = (size_t)32 << 20;
+
+void parallel_memcpy(void *dst, const void *src, size_t bytes, int T) {
+    if (T <= 1 || bytes < ((size_t)4 << 20)) { memcpy(dst, src, bytes); return; }
+    std::vector<std::thread> workers;
+    const size_t slice = ((bytes / T) + 4095) & ~(size_t)4095;
+    for (int k = 1; k < T; k++) {
+        const size_t lo = std::min(bytes, slice * k), hi = std::min(bytes, slice * (k + 1));
+        if (lo < hi) workers.emplace_back([=] { memcpy((char *)dst + lo, (const char *)src + lo, hi - lo); });
+    }
+    memcpy(dst, src, std::min(bytes, slice));
+    for (auto &w : workers) w.join();
+}
+
+int host_copy(tfhe_b200_ctx *c, Device &d, void *dst, const void *src, size_t bytes, cudaMemcpyKind kind) {
+    const void *host = kind == cudaMemcpyHostToDevice ? src : dst;
+    bool staged = c->host_copy_threads > 0 && bytes >= kStagePiece;
+    if (staged) {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); staged = false; }
+        else staged = at.type == cudaMemoryTypeUnregistered;
+    }
+    if (!staged) {
+        CU(c, cudaMemcpyAsync(dst, src, bytes, kind, d.stream));
+        return 0;
+    }
+    for (int k = 0; k < 2; k++) {
+        if (!d.stage[k]) CU(c, cudaHostAlloc(&d.stage[k], kStagePiece, cudaHostAllocPortable));
+        if (!d.stage_ev[k]) CU(c, cudaEventCreateWithFlags(&d.stage_ev[k], cudaEventDisableTiming));
+    }
+    const int T = c->host_copy_threads;
+    const size_t pieces = (bytes + kStagePiece - 1) / kStagePiece;
+    if (kind == cudaMemcpyHostToDevice) {
+        for (size_t p = 0; p < pieces; p++) {
+            const size_t off = p * kStagePiece, nb = std::min(kStagePiece, bytes - off);
+            const int k = (int)(p & 1);
+            if (p >= 2) CU(c, cudaEventSynchronize(d.stage_ev[k]));          // the DMA that last read this staging buffer
+            parallel_memcpy(d.stage[k], (const char *)src + off, nb, T);
+            CU(c, cudaMemcpyAsync((char *)dst + off, d.stage[k], nb, cudaMemcpyHostToDevice, d.stream));
+            CU(c, cudaEventRecord(d.stage_ev[k], d.stream));
+        }
+        CU(c, cudaEventSynchronize(d.stage_ev[(pieces - 1) & 1]));              // staging buffers are free again for the next call
+        if (pieces > 1) CU(c, cudaEventSynchronize(d.stage_ev[(pieces - 2) & 1]));
+    } else {
+        for (size_t p = 0; p < pieces + 1; p++) {                               // DMA of piece p overlaps the memcpy of piece p - 1
+            if (p < pieces) {
+                const size_t off = p * kStagePiece, nb = std::min(kStagePiece, bytes - off);
+                CU(c, cudaMemcpyAsync(d.stage[p & 1], (const char *)src + off, nb, cudaMemcpyDeviceToHost, d.stream));
+                CU(c, cudaEventRecord(d.stage_ev[p & 1], d.stream));
+            }
+            if (p >= 1) {
+                const size_t q = p - 1, off = q * kStagePiece, nb = std::min(kStagePiece, bytes - off);
+                CU(c, cudaEventSynchronize(d.stage_ev[q & 1]));
+                parallel_memcpy((char *)dst + off, d.stage[q & 1], nb, T);
+            }
+        }
+    }
+    return 0;
+}
+
 // host-buffer driver: shard contiguously over devices; every device is driven by its own host thread (chunk, stage,
 // launch, copy back), the stand-in for the reference's CPU thread pool (src/parallel/thread_pool.zig:39-83).  Copies
 // from pageable host memory block the issuing thread, so one thread per device is what lets the H2D / D2H traffic of
@@ -212,10 +284,10 @@ int run_host_device(tfhe_b200_ctx *c, Device &d, size_t lo, size_t hi, int op, c
         const size_t nb = std::min(c->max_chunk, hi - off);
         CU(c, cudaSetDevice(d.id));
         if (int r = ensure(c, d.a, nb * w0 * 4)) return r;
-        CU(c, cudaMemcpyAsync(d.a.p, a + off * w0, nb * w0 * 4, cudaMemcpyHostToDevice, d.stream));
+        if (int r = host_copy(c, d, d.a.p, a + off * w0, nb * w0 * 4, cudaMemcpyHostToDevice)) return r;
         if (two_inputs) {
             if (int r = ensure(c, d.b, nb * w0 * 4)) return r;
-            CU(c, cudaMemcpyAsync(d.b.p, b + off * w0, nb * w0 * 4, cudaMemcpyHostToDevice, d.stream));
+            if (int r = host_copy(c, d, d.b.p, b + off * w0, nb * w0 * 4, cudaMemcpyHostToDevice)) return r;
         }
         const int32_t *d_ops = nullptr;
         if (ops) {
@@ -253,7 +325,7 @@ int run_host_device(tfhe_b200_ctx *c, Device &d, size_t lo, size_t hi, int op, c
             if (!r) CU(c, launch_extract2((uint32_t *)d.lv1.p, d_out, (uint32_t)nb, c->prm.n, d.stream, &d.launches));
         }
         if (r) return r;
-        CU(c, cudaMemcpyAsync((uint32_t *)out + off * wout, d.out.p, nb * wout * 4, cudaMemcpyDeviceToHost, d.stream));
+        if (int r2 = host_copy(c, d, (uint32_t *)out + off * wout, d.out.p, nb * wout * 4, cudaMemcpyDeviceToHost)) return r2;
         CU(c, cudaStreamSynchronize(d.stream));
     }
     return 0;
@@ -501,6 +573,10 @@ void tfhe_b200_destroy(tfhe_b200_ctx *c) {
                         d.out.p, d.lv1.p, d.ops.p, d.tv.p, d.trlwe.p, d.lut.p, d.ksdig.p})
             if (p) cudaFree(p);
         for (cudaEvent_t e : d.ev) if (e) cudaEventDestroy(e);
+        for (int k = 0; k < 2; k++) {
+            if (d.stage[k]) cudaFreeHost(d.stage[k]);
+            if (d.stage_ev[k]) cudaEventDestroy(d.stage_ev[k]);
+        }
         if (d.stream) cudaStreamDestroy(d.stream);
     }
     delete c;
@@ -1041,6 +1117,7 @@ int tfhe_b200_set_tuning(tfhe_b200_ctx *c, const char *key, int value) {
     else if (!strcmp(key, "ks_vec")) c->ks_vec = value;
     else if (!strcmp(key, "ks_fill")) c->ks_fill = value;
     else if (!strcmp(key, "ks_rot")) c->ks_rot = value;
+    else if (!strcmp(key, "host_copy_threads")) c->host_copy_threads = std::max(0, std::min(value, 16));
     else if (!strcmp(key, "ks_tc")) c->ks_tc = value;
     else if (!strcmp(key, "ks_tc_min")) c->ks_tc_min = value;
     else if (!strcmp(key, "exact_legacy")) c->exact_legacy = value != 0;
