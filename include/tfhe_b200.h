@@ -198,6 +198,11 @@ int tfhe_b200_not_batch(tfhe_b200_ctx *ctx, const uint32_t *a, uint32_t *out, si
  * topological order.  TFHE_B200_WIRE_NOT on a wire reference is Gates.notGate (src/gates.zig:131-133) of that wire:
  * free, folded into the consuming gate's linear part (or applied on the way out for a circuit output). */
 #define TFHE_B200_WIRE_NOT 0x80000000u
+/* Gates.constant(true) / Gates.constant(false) (src/gates.zig:144-151) as wires: trivial ciphertexts (mask 0, body 2^29 resp.
+ * 1 - 2^29 = 0xE0000001, the reference's value) that the executor materialises on the device; usable wherever a wire id is,
+ * also under TFHE_B200_WIRE_NOT and as a circuit output.  Gates.copy (src/gates.zig:138-141) is the wire itself. */
+#define TFHE_B200_WIRE_TRUE 0x7FFFFFFEu
+#define TFHE_B200_WIRE_FALSE 0x7FFFFFFDu
 typedef struct {
     int32_t op;  /* tfhe_b200_gate */
     uint32_t a;  /* wire id | TFHE_B200_WIRE_NOT */

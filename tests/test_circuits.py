@@ -303,3 +303,43 @@ def test_circuit_graph_is_recaptured_after_rekey_and_mode_switch():
         circ.close()
     finally:
         ctx.close()
+
+
+def test_circuit_plan_accepts_constant_wires():
+    import tfhe_b200
+    T, F, NOT = tfhe_b200.WIRE_TRUE, tfhe_b200.WIRE_FALSE, tfhe_b200.WIRE_NOT
+    levels, width, gl = tfhe_b200.circuit_plan([(O.AND, 0, T), (O.OR, 2, F | NOT), (O.NAND, T, F)], 2, [3, T, F | NOT])
+    assert (levels, width) == (2, 2) and list(gl) == [1, 2, 1]
+    assert tfhe_b200.circuit_plan([(O.XOR, T, F)], 0, [0])[:2] == (1, 1)            # no inputs at all: wire 0 is the gate
+
+
+@pytest.mark.gpu
+def test_constant_wires_in_circuits_match_gates_constant():
+    """Gates.constant (src/gates.zig:144-151) as circuit wires: (0, 2^29) and the reference's (0, 1 - 2^29); as gate operands,
+    negated, and as outputs; word for word against the oracle's gate_constant + gates"""
+    import tfhe_b200
+    orc = O.Oracle("128"); keys = keys_for("128")
+    ctx = tfhe_b200.Context("128", devices=[0])
+    try:
+        ctx.load_key(keys.bsk, keys.ksk, keys.offset)
+        T, F, NOT = tfhe_b200.WIRE_TRUE, tfhe_b200.WIRE_FALSE, tfhe_b200.WIRE_NOT
+        bits = np.array([0, 1, 1, 0, 1], np.uint8)
+        ca = orc.encrypt_bools(bits, keys, 61)
+        gates = [(O.AND, 0, T), (O.OR, 0, F), (O.XOR, 0, T | NOT), (O.NAND, T, F), (O.ANDNY, 1, T)]
+        outs = [1, 2, 3, 4, 5, T, F, F | NOT]
+        circ = tfhe_b200.Circuit(ctx, gates, 1, outs)
+        assert circ.levels == 2
+        got = circ.run(ca[None])
+        B = len(bits)
+        ct = np.stack([orc.gate_constant(True)] * B); cf = np.stack([orc.gate_constant(False)] * B)
+        neg = lambda c: (0 - c.astype(np.int64)).astype(np.uint32)
+        w1 = orc.gate_batch(O.AND, ca, ct, keys)
+        want = [w1, orc.gate_batch(O.OR, ca, cf, keys), orc.gate_batch(O.XOR, ca, neg(ct), keys), orc.gate_batch(O.NAND, ct, cf, keys),
+                orc.gate_batch(O.ANDNY, w1, ct, keys), ct, cf, neg(cf)]
+        for k, w in enumerate(want):
+            assert (got[k] == w).all(), f"output {k}"
+        assert (orc.decrypt_bools(got[0], keys) == bits).all() and (orc.decrypt_bools(got[3], keys) == 1).all()
+        assert got[6][0, -1] == 0xE0000001 and got[5][0, -1] == 0x20000000
+        circ.close()
+    finally:
+        ctx.close()

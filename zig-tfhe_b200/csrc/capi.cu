@@ -441,6 +441,7 @@ int upload_key_device(tfhe_b200_ctx *c, Device &d, const double *src_bsk, bool b
 struct tfhe_b200_circuit {
     tfhe_b200_ctx *ctx = nullptr;
     size_t n_inputs = 0, n_gates = 0, n_slots = 0, max_width = 0;
+    bool has_consts = false;         // slots n_inputs (true) and n_inputs + 1 (false) hold Gates.constant wires
     struct Level { uint32_t first_slot, G; size_t off; };
     std::vector<Level> levels;
     std::vector<int32_t> ops;        // level-sorted gate tables (slot references, bit 31 = NOT)
@@ -846,10 +847,11 @@ static int circuit_plan(const tfhe_b200_gate_node *gates, size_t n_gates, size_t
     char buf[160];
     const size_t n_wires = n_inputs + n_gates;
     if ((!gates && n_gates) || (!outputs && n_outputs)) { why = "null argument"; return TFHE_B200_ERR_INVALID; }
-    if (n_wires == 0 || n_wires >= 0x7fffffffu) { why = "bad circuit size"; return TFHE_B200_ERR_INVALID; }
+    if (n_wires == 0 || n_wires >= TFHE_B200_WIRE_FALSE) { why = "bad circuit size"; return TFHE_B200_ERR_INVALID; }
     const uint32_t kNot = TFHE_B200_WIRE_NOT;
     level.assign(n_wires, 0);
     depth = 0;
+    auto is_const = [](uint32_t w) { return w == TFHE_B200_WIRE_TRUE || w == TFHE_B200_WIRE_FALSE; };
     for (size_t g = 0; g < n_gates; g++) {
         const uint32_t a = gates[g].a & ~kNot, b = gates[g].b & ~kNot;
         if (gates[g].op < 0 || gates[g].op > 9) {
@@ -857,16 +859,17 @@ static int circuit_plan(const tfhe_b200_gate_node *gates, size_t n_gates, size_t
             why = buf;
             return TFHE_B200_ERR_INVALID;
         }
-        if (a >= n_inputs + g || b >= n_inputs + g) {
+        if ((!is_const(a) && a >= n_inputs + g) || (!is_const(b) && b >= n_inputs + g)) {
             snprintf(buf, sizeof(buf), "gate %zu reads a wire defined later (not topological)", g);
             why = buf;
             return TFHE_B200_ERR_INVALID;
         }
-        level[n_inputs + g] = 1 + std::max(level[a], level[b]);
+        // constants sit at level 0 like the inputs (Gates.constant needs no bootstrap, src/gates.zig:144-151)
+        level[n_inputs + g] = 1 + std::max(is_const(a) ? 0u : level[a], is_const(b) ? 0u : level[b]);
         depth = std::max(depth, level[n_inputs + g]);
     }
     for (size_t o = 0; o < n_outputs; o++)
-        if ((outputs[o] & ~kNot) >= n_wires) {
+        if ((outputs[o] & ~kNot) >= n_wires && !is_const(outputs[o] & ~kNot)) {
             snprintf(buf, sizeof(buf), "output %zu: no such wire", o);
             why = buf;
             return TFHE_B200_ERR_INVALID;
@@ -904,13 +907,23 @@ int tfhe_b200_circuit_create(tfhe_b200_ctx *c, const tfhe_b200_gate_node *gates,
     }
     auto *q = new tfhe_b200_circuit();
     q->ctx = c;
-    q->n_inputs = n_inputs; q->n_gates = n_gates; q->n_slots = n_wires;
-    // storage slots: inputs first, then gates level by level, so that a level's outputs are one contiguous block
+    auto is_const = [](uint32_t w) { return (w & ~TFHE_B200_WIRE_NOT) == TFHE_B200_WIRE_TRUE || (w & ~TFHE_B200_WIRE_NOT) == TFHE_B200_WIRE_FALSE; };
+    for (size_t g = 0; g < n_gates; g++) q->has_consts = q->has_consts || is_const(gates[g].a) || is_const(gates[g].b);
+    for (size_t o = 0; o < n_outputs; o++) q->has_consts = q->has_consts || is_const(outputs[o]);
+    const uint32_t n_const = q->has_consts ? 2u : 0u;
+    q->n_inputs = n_inputs; q->n_gates = n_gates; q->n_slots = n_wires + n_const;
+    // storage slots: inputs first, then the two Gates.constant wires (if any gate or output uses one), then the gates level
+    // by level, so that a level's outputs are one contiguous block
     std::vector<uint32_t> slot(n_wires);
     for (size_t i = 0; i < n_inputs; i++) slot[i] = (uint32_t)i;
+    auto slot_of = [&](uint32_t ref) -> uint32_t {
+        const uint32_t w = ref & ~kNot;
+        const uint32_t sl = w == TFHE_B200_WIRE_TRUE ? (uint32_t)n_inputs : w == TFHE_B200_WIRE_FALSE ? (uint32_t)n_inputs + 1u : slot[w];
+        return sl | (ref & kNot);
+    };
     std::vector<std::vector<uint32_t>> by_level(depth + 1);
     for (size_t g = 0; g < n_gates; g++) by_level[level[n_inputs + g]].push_back((uint32_t)g);
-    uint32_t next = (uint32_t)n_inputs;
+    uint32_t next = (uint32_t)n_inputs + n_const;
     for (uint32_t l = 1; l <= depth; l++) {
         q->levels.push_back({next, (uint32_t)by_level[l].size(), q->ops.size()});
         q->max_width = std::max(q->max_width, by_level[l].size());
@@ -922,10 +935,10 @@ int tfhe_b200_circuit_create(tfhe_b200_ctx *c, const tfhe_b200_gate_node *gates,
         }
     }
     for (size_t k = 0; k < q->wa.size(); k++) {
-        q->wa[k] = slot[q->wa[k] & ~kNot] | (q->wa[k] & kNot);
-        q->wb[k] = slot[q->wb[k] & ~kNot] | (q->wb[k] & kNot);
+        q->wa[k] = slot_of(q->wa[k]);
+        q->wb[k] = slot_of(q->wb[k]);
     }
-    for (size_t o = 0; o < n_outputs; o++) q->outputs.push_back(slot[outputs[o] & ~kNot] | (outputs[o] & kNot));
+    for (size_t o = 0; o < n_outputs; o++) q->outputs.push_back(slot_of(outputs[o]));
     q->lanes = std::max(1, std::min(c->circuit_lanes, 8));
     q->dev.resize(c->devs.size() * q->lanes);
     for (size_t k = 0; k < c->devs.size(); k++) {
@@ -1007,6 +1020,10 @@ static int circuit_run_device(tfhe_b200_ctx *c, tfhe_b200_circuit *q, int k, con
             uint32_t *wires = (uint32_t *)pd.wires.p;
             for (size_t i = 0; i < q->n_inputs; i++)
                 CU(c, cudaMemcpyAsync(wires + i * inst * w0, inputs + (i * instances + pos[l]) * w0, inst * w0 * 4, cudaMemcpyHostToDevice, pd.stream));
+            if (q->has_consts) {   // Gates.constant(true) = (0, 2^29), Gates.constant(false) = (0, 1 - 2^29) (src/gates.zig:146-147)
+                CU(c, launch_fill_constant(wires + q->n_inputs * inst * w0, inst, (int)w0, 0x20000000u, pd.stream, &d.launches));
+                CU(c, launch_fill_constant(wires + (q->n_inputs + 1) * inst * w0, inst, (int)w0, 0xE0000001u, pd.stream, &d.launches));
+            }
             if (int r = circuit_enqueue(c, q, d, pd, inst)) return r;
         }
         for (int l = 0; l < nl; l++) {          // results back (a pageable D2H blocks this thread until the lane is done)

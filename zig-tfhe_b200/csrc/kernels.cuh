@@ -102,6 +102,8 @@ cudaError_t launch_keygen_bsk(const uint32_t *s0, const uint32_t *s1, uint64_t s
                               const cplx *tw3, cplx *dev, double *ref, cudaStream_t s, uint64_t *launches);
 // K3: out = -a over [B][n+1]
 cudaError_t launch_negate(const uint32_t *a, uint32_t *out, size_t count, cudaStream_t s, uint64_t *launches);
+// n_rows trivial ciphertexts (mask 0, body `body`) of w words each: Gates.constant (src/gates.zig:144-151)
+cudaError_t launch_fill_constant(uint32_t *rows, size_t n_rows, int w, uint32_t body, cudaStream_t s, uint64_t *launches);
 // first n entries + body of an lv1 sample -> TLWELv0-shaped "hybrid" sample (trlwe.zig:165-180)
 cudaError_t launch_extract2(const uint32_t *lv1, uint32_t *out, uint32_t B, int n, cudaStream_t s, uint64_t *launches);
 

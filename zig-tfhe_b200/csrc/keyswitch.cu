@@ -173,6 +173,12 @@ __global__ void negate_kernel(const uint32_t *a, uint32_t *out, size_t count) {
     if (i < count) out[i] = 0u - a[i];
 }
 
+// trivial ciphertexts of Gates.constant (src/gates.zig:144-151): rows of w words, mask 0, body `body`
+__global__ void fill_constant_kernel(uint32_t *rows, size_t count, int w, uint32_t body) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) rows[i] = ((int)(i % (size_t)w) == w - 1) ? body : 0u;
+}
+
 __global__ void extract2_kernel(const uint32_t *lv1, uint32_t *out, uint32_t B, int n) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t w = (size_t)n + 1;
@@ -228,6 +234,14 @@ cudaError_t launch_repack_ksk(const uint32_t *ref_ksk, size_t ref_row_stride_u32
 cudaError_t launch_negate(const uint32_t *a, uint32_t *out, size_t count, cudaStream_t s, uint64_t *launches) {
     if (!count) return cudaSuccess;
     negate_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(a, out, count);
+    if (launches) (*launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fill_constant(uint32_t *rows, size_t n_rows, int w, uint32_t body, cudaStream_t s, uint64_t *launches) {
+    if (!n_rows) return cudaSuccess;
+    const size_t count = n_rows * (size_t)w;
+    fill_constant_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(rows, count, w, body);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }

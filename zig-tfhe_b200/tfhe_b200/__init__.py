@@ -433,6 +433,7 @@ class Context:
 
 
 WIRE_NOT = 0x80000000
+WIRE_TRUE, WIRE_FALSE = 0x7FFFFFFE, 0x7FFFFFFD    # Gates.constant(true / false) as circuit wires (gates.zig:144-151)
 
 GATE_NODE = np.dtype([("op", np.int32), ("a", np.uint32), ("b", np.uint32)])
 

@@ -64,11 +64,15 @@ pub extern fn tfhe_b200_load_reencryption_key(ctx: *Ctx, key: [*]const u32, base
 pub extern fn tfhe_b200_reencrypt_batch(ctx: *Ctx, in: [*]const u32, out: [*]u32, count: usize) c_int;
 pub extern fn tfhe_b200_not_batch(ctx: *Ctx, a: [*]const u32, out: [*]u32, count: usize) c_int;
 pub extern fn tfhe_b200_sync(ctx: *Ctx) c_int;
+/// tuning keys are listed in include/tfhe_b200.h ("kct", "twt", "ks_tc", "host_copy_threads", "circuit_lanes", ...)
+pub extern fn tfhe_b200_set_tuning(ctx: *Ctx, key: [*:0]const u8, value: c_int) c_int;
 
 /// gate circuits (include/tfhe_b200.h): a netlist levelised once, every level one batched launch pair over
 /// (gates of the level) x (instances) -- the batched form of examples/add_two_numbers.zig:24-73
 pub const Circuit = opaque {};
 pub const wire_not: u32 = 0x80000000; // Gates.notGate of the referenced wire, folded into the consumer
+pub const wire_true: u32 = 0x7FFFFFFE; // Gates.constant(true), src/gates.zig:144-151
+pub const wire_false: u32 = 0x7FFFFFFD; // Gates.constant(false) = (0, 1 - 2^29)
 pub const GateNode = extern struct { op: i32, a: u32, b: u32 };
 pub extern fn tfhe_b200_circuit_create(ctx: *Ctx, gates: [*]const GateNode, n_gates: usize, n_inputs: usize, outputs: [*]const u32, n_outputs: usize, out: *?*Circuit) c_int;
 pub extern fn tfhe_b200_circuit_destroy(circuit: ?*Circuit) void;

@@ -9,6 +9,7 @@ const params = @import("../params.zig");
 const utils = @import("../utils.zig");
 const key = @import("../key.zig");
 const tlwe = @import("../tlwe.zig");
+const lut = @import("../lut.zig");
 const cuda = @import("../cuda.zig");
 
 const n = params.implementation.tlwe_lv0.N;
@@ -79,6 +80,46 @@ pub const GpuBootstrap = struct {
     pub fn name(self: *const Self) []const u8 {
         _ = self;
         return "b200";
+    }
+
+    /// The `bootstrapLut` src/lut.zig:42 documents and the reference never defines: programmable bootstrap of one
+    /// ciphertext with a lookup table from lut.Generator (src/lut/generator.zig:85-135): blindRotateWithTestvec
+    /// (src/trgsw.zig:336-400) -> sampleExtractIndex(., 0) -> identityKeySwitching, all on the device.
+    pub fn bootstrapLut(self: *const Self, ctxt: *const utils.Ciphertext, table: *const lut.LookupTable) !utils.Ciphertext {
+        var tv: [2 * N]u32 = undefined; // TRLWELv1 packed: a then b (src/trlwe.zig:15-17)
+        @memcpy(tv[0..N], &table.poly.a);
+        @memcpy(tv[N .. 2 * N], &table.poly.b);
+        var out = utils.Ciphertext.new();
+        try cuda.check(cuda.tfhe_b200_bootstrap_batch(self.ctx, &ctxt.p, &out.p, 1, &tv, 0));
+        return out;
+    }
+
+    /// `count` programmable bootstraps in one call.  `tables`: torus values Encoder.encode(f(x)), x < message_modulus
+    /// (src/lut/encoder.zig:66-73), one table shared by all items (tables.len == message_modulus) or one per item
+    /// (tables.len == count * message_modulus); the test vectors are built on the device (generator.zig:150-191).
+    /// Caller-freed result slice, like gates.batch*.
+    pub fn batchLut(
+        self: *const Self,
+        allocator: std.mem.Allocator,
+        inputs: []const utils.Ciphertext,
+        tables: []const params.Torus,
+        message_modulus: usize,
+    ) ![]utils.Ciphertext {
+        const count = inputs.len;
+        std.debug.assert(tables.len == message_modulus or tables.len == count * message_modulus);
+        const in_words = try allocator.alloc(u32, count * CT_WORDS);
+        defer allocator.free(in_words);
+        const out_words = try allocator.alloc(u32, count * CT_WORDS);
+        defer allocator.free(out_words);
+        for (inputs, 0..) |*c, i| @memcpy(in_words[i * CT_WORDS .. (i + 1) * CT_WORDS], &c.p);
+        const per_item: c_int = if (tables.len == message_modulus) 0 else 1;
+        try cuda.check(cuda.tfhe_b200_lut_bootstrap_batch(self.ctx, in_words.ptr, out_words.ptr, count, tables.ptr, @intCast(message_modulus), per_item));
+        const result = try allocator.alloc(utils.Ciphertext, count);
+        for (result, 0..) |*r, i| {
+            r.* = utils.Ciphertext.new();
+            @memcpy(&r.p, out_words[i * CT_WORDS .. (i + 1) * CT_WORDS]);
+        }
+        return result;
     }
 
     /// Body for gates.batchNand/And/Or/Xor/Nor/Xnor (src/gates.zig:244-295): same signature shape
@@ -156,3 +197,40 @@ pub const GpuBootstrap = struct {
         return result;
     }
 };
+
+/// Process-wide device context for the free functions of src/gates.zig (batchNand ... batchXnor take only the cloud key):
+/// created on first use for the cloud key it is first called with, on every visible GPU unless TFHE_B200_DEVICES=<count>
+/// says otherwise; a different cloud key replaces the keys on the device.  Guarded by a mutex because the reference lets any
+/// thread call gates with a shared *const CloudKey (src/fft.zig:983-992 keeps its only hidden state per thread); the device
+/// context itself is not thread-safe, so batch calls through the singleton are serialised.
+var singleton: ?GpuBootstrap = null;
+var singleton_key: ?*const key.CloudKey = null;
+var singleton_mutex: std.Thread.Mutex = .{};
+
+pub fn gpu_singleton(cloud_key: *const key.CloudKey) !*GpuBootstrap {
+    singleton_mutex.lock();
+    defer singleton_mutex.unlock();
+    if (singleton != null and singleton_key == cloud_key) return &singleton.?;
+    if (singleton) |*old| {
+        old.deinit();
+        singleton = null;
+    }
+    var ids: [16]c_int = undefined;
+    var count: usize = 1;
+    if (std.posix.getenv("TFHE_B200_DEVICES")) |v| {
+        count = @min(ids.len, @max(1, std.fmt.parseInt(usize, v, 10) catch 1));
+    }
+    for (0..count) |i| ids[i] = @intCast(i);
+    singleton = try GpuBootstrap.init(std.heap.page_allocator, cloud_key, ids[0..count]);
+    singleton_key = cloud_key;
+    return &singleton.?;
+}
+
+/// serialises a batch call through the singleton (see above)
+pub fn batchGateShared(op: cuda.Gate, inputs: []const struct { utils.Ciphertext, utils.Ciphertext }, cloud_key: *const key.CloudKey) ![]utils.Ciphertext {
+    const g = try gpu_singleton(cloud_key);
+    singleton_mutex.lock();
+    defer singleton_mutex.unlock();
+    // results come from page_allocator, as the reference's parallel module returns them (src/parallel/thread_pool.zig:55)
+    return g.batchGate(std.heap.page_allocator, op, inputs);
+}
