@@ -61,3 +61,27 @@ def test_circuit_shards_instances_over_devices_and_lanes():
         q1.close(); q2.close()
     finally:
         c1.close(); c2.close()
+
+
+def test_failure_on_one_device_of_a_multi_device_context():
+    """a shard failing on device 1 while device 0 works: the call fails as a whole (err_mu-guarded message from the failing
+    thread), nothing hangs, and the context computes correctly afterwards"""
+    import torch
+    import tfhe_b200
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    orc = O.Oracle("128"); keys = keys_for("128")
+    c = tfhe_b200.Context("128", devices=[0, 1])
+    try:
+        c.load_key(keys.bsk, keys.ksk, keys.offset)
+        bits = (np.arange(300) % 2).astype(np.uint8)
+        ca = orc.encrypt_bools(bits, keys, 5); cb = orc.encrypt_bools(1 - bits, keys, 6)
+        c.set_tuning("inject_fault", 2)
+        with pytest.raises(tfhe_b200.TfheB200Error, match="injected fault on device 1"):
+            c.gate_batch(O.OR, ca, cb)
+        out = c.gate_batch(O.OR, ca, cb)
+        assert (orc.decrypt_bools(out, keys) == 1).all()
+        sel = np.array([0, 149, 150, 299])
+        assert (out[sel] == orc.gate_batch(O.OR, ca[sel], cb[sel], keys)).all()
+    finally:
+        c.close()

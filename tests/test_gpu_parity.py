@@ -303,3 +303,15 @@ def test_tensor_core_keyswitch_bit_exact(name):
         assert (out[sel] == orc.gate_batch(O.NAND, ca[sel], cb[sel], k)).all()
     finally:
         c.close()
+
+
+def test_a_failing_shard_reports_and_the_context_survives(ctx128, orc128, keys128):
+    """error path of the host-batch driver: one device's shard fails (test hook) -> the call returns the error with its
+    message, other shards are joined, and the next call on the same context gives the right bits again"""
+    import tfhe_b200
+    a, b, ca, cb = _enc_pairs(orc128, keys128, 64, seed=31)
+    good = ctx128.gate_batch(O.NAND, ca, cb)
+    ctx128.set_tuning("inject_fault", 1)
+    with pytest.raises(tfhe_b200.TfheB200Error, match="injected fault"):
+        ctx128.gate_batch(O.NAND, ca, cb)
+    assert (ctx128.gate_batch(O.NAND, ca, cb) == good).all()

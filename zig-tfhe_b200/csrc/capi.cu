@@ -67,6 +67,7 @@ struct tfhe_b200_ctx {
     uint64_t launches = 0;
     bool timing = false;
     int ks_tile = 0, ks_vec = 0, ks_fill = 0, ks_rot = 0;   // key-switch tuning overrides (0 = automatic)
+    int inject_fault = 0;                 // test hook (tuning key "inject_fault"): device k = value - 1 fails its next host-batch shard
     int host_copy_threads = 8;            // large copies from / to PAGEABLE caller memory are staged through pinned buffers by this many
                                           // memcpy threads (0 = plain cudaMemcpyAsync from the caller's buffer)
     int ks_tc = 0;                        // tensor-core key switch: 0 = automatic (batches >= ks_tc_min), 1 = always, -1 = never
@@ -280,6 +281,10 @@ int run_host_device(tfhe_b200_ctx *c, Device &d, size_t lo, size_t hi, int op, c
     const size_t w0 = (size_t)c->prm.n + 1, w1 = (size_t)kN + 1, wt = (size_t)2 * kN;
     const size_t wout = (kind == Out::LV0 || kind == Out::LV0_NOKS) ? w0 : (kind == Out::LV1) ? w1 : wt;
     const bool two_inputs = (op >= 0 || ops);
+    if (c->inject_fault > 0 && &d == &c->devs[(size_t)(c->inject_fault - 1) % c->devs.size()]) {
+        c->inject_fault = 0;       // one shot: the context must be usable again afterwards
+        return fail(c, TFHE_B200_ERR_CUDA, "injected fault on device %d (test hook)", d.id);
+    }
     for (size_t off = lo; off < hi; off += c->max_chunk) {
         const size_t nb = std::min(c->max_chunk, hi - off);
         CU(c, cudaSetDevice(d.id));
@@ -1134,6 +1139,7 @@ int tfhe_b200_set_tuning(tfhe_b200_ctx *c, const char *key, int value) {
     else if (!strcmp(key, "ks_vec")) c->ks_vec = value;
     else if (!strcmp(key, "ks_fill")) c->ks_fill = value;
     else if (!strcmp(key, "ks_rot")) c->ks_rot = value;
+    else if (!strcmp(key, "inject_fault")) c->inject_fault = value;
     else if (!strcmp(key, "host_copy_threads")) c->host_copy_threads = std::max(0, std::min(value, 16));
     else if (!strcmp(key, "ks_tc")) c->ks_tc = value;
     else if (!strcmp(key, "ks_tc_min")) c->ks_tc_min = value;
