@@ -164,6 +164,16 @@ int tfhe_b200_bootstrap_batch(tfhe_b200_ctx *ctx, const uint32_t *in, uint32_t *
  * runs on the device, then the `bootstrapLut` src/lut.zig:42 documents.  tables: [B][message_modulus] (per_item != 0)
  * or [message_modulus] torus values, entry x = the output for message x (Encoder.encode(f(x)), src/lut/encoder.zig:66-73).
  * Per-item tables cost message_modulus words of host-to-device traffic per item instead of an 8 KiB test vector. */
+/* SEVERAL functions from ONE blind rotation (the reference has no such call).  tables:
+ * [n_functions][message_modulus] torus values as above, n_functions a power of two with n_functions * 2 * message_modulus <= N.
+ * The test vector interleaves the functions' lookup tables (position n_functions * i + f = table f at position
+ * n_functions * i), the modulus switch of blindRotate (src/trgsw.zig:297,312) rounds to multiples of n_functions, so the
+ * accumulator holds function f at every index congruent to f, and output f is sampleExtractIndex(., f)
+ * (src/trlwe.zig:146-162) followed by identityKeySwitching.  out: [n_functions][B][n+1].  Cost: one blind rotation plus
+ * n_functions key switches per item; the coarser switch adds up to n_functions / 2 positions of rounding error, to be kept
+ * well inside the N / (2 * message_modulus) half-slot. */
+int tfhe_b200_lut_bootstrap_many_batch(tfhe_b200_ctx *ctx, const uint32_t *in, uint32_t *out, size_t B, const uint32_t *tables,
+                                       int n_functions, int message_modulus);
 int tfhe_b200_lut_bootstrap_batch(tfhe_b200_ctx *ctx, const uint32_t *in, uint32_t *out, size_t B, const uint32_t *tables,
                                   int message_modulus, int per_item);
 /* parity tap: the device-built LookupTable.poly [2][N] of one table (src/lut/lookup_table.zig:16-20) */

@@ -108,3 +108,46 @@ def test_device_lut_generator_and_table_bootstrap():
         assert (one == c.bootstrap_batch(ct, tvs[2])).all()
     finally:
         c.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,m,k", [("128", 4, 4), ("128", 4, 2), ("uint1", 2, 8)])
+def test_many_function_bootstrap(name, m, k):
+    """several functions from one blind rotation (tfhe_b200_lut_bootstrap_many_batch): every output decodes f_j(message), and
+    equals, word for word, the oracle's blindRotateWithTestvec on the interleaved test vector fed with the input rounded to
+    the coarse modulus-switch grid, sampleExtractIndex(., j), identityKeySwitching (src/trgsw.zig:336-400, 471-502,
+    src/trlwe.zig:146-162)"""
+    import tfhe_b200
+    from conftest import keys_for
+    orc = O.Oracle(name); keys = keys_for(name)
+    c = tfhe_b200.Context(name, devices=[0])
+    try:
+        c.load_key(keys.bsk, keys.ksk, keys.offset)
+        if name != "128":
+            c.set_mode(tfhe_b200.MODE_EXACT)
+        B = 300
+        rng = np.random.default_rng(4)
+        msgs = rng.integers(0, m, B).astype(np.uint32)
+        ct = orc.encrypt_lwe_messages(msgs, m, keys, seed=9)
+        funcs = [np.array([(x * (j + 1) + j) % m for x in range(m)], np.uint32) for j in range(k)]
+        tables = np.stack([np.array([O.lut_encode(int(v), m) for v in f], np.uint32) for f in funcs])
+        got = c.lut_bootstrap_many_batch(ct, tables)
+        assert got.shape == (k, B, orc.n + 1)
+        for j in range(k):
+            assert (orc.decrypt_lwe_messages(got[j], m, keys) == funcs[j][msgs]).all(), f"function {j}"
+        # oracle emulation on a sample: pre-round the input to multiples of k * 2^21, interleave the test vectors
+        shift = k.bit_length() - 1
+        sel = np.arange(0, B, 37)
+        pre = (((ct[sel].astype(np.uint64) + (1 << (20 + shift))) >> (21 + shift)) << (21 + shift)).astype(np.uint32)
+        tv = np.zeros((2, 1024), np.uint32)
+        for j in range(k):
+            tj = orc.lut_generate(funcs[j], m)
+            tv[1, j::k] = tj[1, 0::k]
+        tr = orc.blind_rotate_batch(pre, keys, tv)
+        for j in range(k):
+            lv1 = np.stack([orc.sample_extract_index(t, j) for t in tr])
+            assert (got[j][sel] == orc.keyswitch_batch(lv1, keys)).all(), f"function {j} differs from the oracle"
+        with pytest.raises(tfhe_b200.TfheB200Error):
+            c.lut_bootstrap_many_batch(ct, np.zeros((3, m), np.uint32))      # not a power of two
+    finally:
+        c.close()

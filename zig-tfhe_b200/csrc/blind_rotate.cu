@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
         for (int i = t; i <= n; i += kGroupThreads) {
             uint32_t lin = gate_linear_signed(go, i);
             if (i == n) lin += gate_constant(op);
-            const uint32_t m = (uint32_t)(((unsigned long long)lin + (1u << 20)) >> 21);   // in [0, 2N]
+            const uint32_t m = mod_switch_2n(lin, P.ms_shift);   // in [0, 2N]
             atil[i] = (uint16_t)((i == n) ? (2 * kN - m) : m);
         }
     }
@@ -631,7 +631,7 @@ __global__ void __launch_bounds__(2 * L * kGroupThreads, 1) blind_rotate_latency
         for (int i = tid; i <= n; i += G * kGroupThreads) {
             uint32_t lin = gate_linear_signed(go, i);
             if (i == n) lin += gate_constant(op);
-            const uint32_t m = (uint32_t)(((unsigned long long)lin + (1u << 20)) >> 21);
+            const uint32_t m = mod_switch_2n(lin, P.ms_shift);
             atil[i] = (uint16_t)((i == n) ? (2 * kN - m) : m);
         }
     }
@@ -796,7 +796,7 @@ __global__ void __launch_bounds__(L * kGroupThreads, 1) blind_rotate_pair_kernel
         for (int i = tid; i <= n; i += L * kGroupThreads) {
             uint32_t lin = gate_linear_signed(go, i);
             if (i == n) lin += gate_constant(op);
-            const uint32_t m = (uint32_t)(((unsigned long long)lin + (1u << 20)) >> 21);
+            const uint32_t m = mod_switch_2n(lin, P.ms_shift);
             atil[i] = (uint16_t)((i == n) ? (2 * kN - m) : m);
         }
     }

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(kThreads, 2) blind_rotate_exact_kernel(const B
         for (int i = j; i <= n; i += kThreads) {
             uint32_t lin = gate_linear_signed(go, i);
             if (i == n) lin += gate_constant(op);
-            const uint32_t m = (uint32_t)(((unsigned long long)lin + (1u << 20)) >> 21);
+            const uint32_t m = mod_switch_2n(lin, P.ms_shift);
             atil[i] = (uint16_t)((i == n) ? (2 * kN - m) : m);
         }
     }
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1)
         for (int i = t; i <= n; i += kGroupThreads) {
             uint32_t lin = gate_linear_signed(go, i);
             if (i == n) lin += gate_constant(op);
-            const uint32_t m = (uint32_t)(((unsigned long long)lin + (1u << 20)) >> 21);
+            const uint32_t m = mod_switch_2n(lin, P.ms_shift);
             atil[i] = (uint16_t)((i == n) ? (2 * kN - m) : m);
         }
     }

@@ -106,6 +106,13 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         : "memory");
 }
 
+// modulus switch 2^32 -> 2N of blindRotate (src/trgsw.zig:297,312): (x + 2^20) >> 21 in 64 bits, so 2N itself can occur.
+// shift > 0: the result is a multiple of 2^shift (rounded to it) -- the coarser switch of a many-function bootstrap, whose
+// test vector interleaves 2^shift functions and whose accumulator is sample-extracted at indices 0 .. 2^shift - 1.
+__device__ __forceinline__ uint32_t mod_switch_2n(uint32_t x, int shift) {
+    return (uint32_t)((((unsigned long long)x + (1ull << (20 + shift))) >> (21 + shift)) << shift);
+}
+
 // linear part of the ten bootstrapped gates (gates.zig:48-121); op < 0: identity (plain bootstrap)
 __device__ __forceinline__ uint32_t gate_linear(int op, uint32_t a, uint32_t b) {
     switch (op) {

@@ -158,7 +158,7 @@ struct LevelRef {            // one dependency level of a circuit: operands are 
 
 int run_device(tfhe_b200_ctx *c, Device &d, int op, const int32_t *d_ops, const uint32_t *d_a, const uint32_t *d_b, uint32_t *d_lv0,
                uint32_t *d_lv1_out, uint32_t *d_trlwe, size_t B, const uint32_t *d_tv, int tv_per_item,
-               const LevelRef *lvl = nullptr, bool concurrent = false, uint64_t *ks_digits = nullptr) {
+               const LevelRef *lvl = nullptr, bool concurrent = false, uint64_t *ks_digits = nullptr, int ms_shift = 0) {
     if (!c->has_key) return fail(c, TFHE_B200_ERR_NO_KEY, "no cloud key loaded");
     if (B == 0) return 0;
     CU(c, cudaSetDevice(d.id));
@@ -176,6 +176,7 @@ int run_device(tfhe_b200_ctx *c, Device &d, int op, const int32_t *d_ops, const 
     A.margin_bits = c->track_margin ? d.margin_bits : nullptr;
     A.B = (uint32_t)B; A.n = c->prm.n; A.L = c->prm.L; A.bgbit = c->prm.bgbit;
     A.offset = c->offset; A.wide_round = wide_round(c->prm) ? 1 : 0;
+    A.ms_shift = ms_shift;
 #ifdef TFHE_B200_DIAG
     A.diag = c->tune.diag;
 #endif
@@ -709,6 +710,72 @@ int tfhe_b200_lut_bootstrap_batch(tfhe_b200_ctx *c, const uint32_t *in, uint32_t
                                   int per_item) {
     if (!c || !tables || message_modulus < 1 || message_modulus > kN) return fail(c, TFHE_B200_ERR_INVALID, "bad lookup table");
     return run_host(c, -1, nullptr, in, nullptr, out, Out::LV0, B, tables, per_item, message_modulus);
+}
+
+// One device's share of a many-function bootstrap: K1 with the coarse modulus switch and the interleaved test vector, then
+// per function sampleExtractIndex(., f) -> key switch.
+static int many_lut_device(tfhe_b200_ctx *c, Device &d, size_t lo, size_t hi, size_t B, const uint32_t *in, uint32_t *out, const uint32_t *tv,
+                           int k, int shift) {
+    const size_t w0 = (size_t)c->prm.n + 1, w1 = (size_t)kN + 1, wt = (size_t)2 * kN;
+    const size_t chunk = std::min<size_t>(c->max_chunk, (size_t)1 << 15);     // 8 KiB of accumulator per ciphertext stays on the device
+    CU(c, cudaSetDevice(d.id));
+    if (int r = ensure(c, d.tv, wt * 4)) return r;
+    CU(c, cudaMemcpyAsync(d.tv.p, tv, wt * 4, cudaMemcpyHostToDevice, d.stream));
+    for (size_t off = lo; off < hi; off += chunk) {
+        const size_t nb = std::min(chunk, hi - off);
+        if (int r = ensure(c, d.a, nb * w0 * 4)) return r;
+        if (int r = ensure(c, d.trlwe, nb * wt * 4)) return r;
+        if (int r = ensure(c, d.lv1, nb * w1 * 4)) return r;
+        if (int r = ensure(c, d.out, nb * w0 * 4)) return r;
+        if (int r = host_copy(c, d, d.a.p, in + off * w0, nb * w0 * 4, cudaMemcpyHostToDevice)) return r;
+        if (int r = run_device(c, d, -1, nullptr, (uint32_t *)d.a.p, nullptr, nullptr, nullptr, (uint32_t *)d.trlwe.p, nb, (const uint32_t *)d.tv.p, 0,
+                               nullptr, false, nullptr, shift))
+            return r;
+        for (int f = 0; f < k; f++) {
+            CU(c, launch_sample_extract((const uint32_t *)d.trlwe.p, (uint32_t *)d.lv1.p, (uint32_t)nb, f, d.stream, &d.launches));
+            if (int r = run_keyswitch(c, d, (const uint32_t *)d.lv1.p, (uint32_t *)d.out.p, nb, nullptr, &d.launches)) return r;
+            if (int r = host_copy(c, d, out + ((size_t)f * B + off) * w0, d.out.p, nb * w0 * 4, cudaMemcpyDeviceToHost)) return r;
+        }
+        CU(c, cudaStreamSynchronize(d.stream));
+    }
+    return 0;
+}
+
+int tfhe_b200_lut_bootstrap_many_batch(tfhe_b200_ctx *c, const uint32_t *in, uint32_t *out, size_t B, const uint32_t *tables, int n_functions,
+                                       int message_modulus) {
+    const int k = n_functions, m = message_modulus;
+    if (!c || !in || !out || !tables || m < 1 || k < 1 || (k & (k - 1)) != 0 || (long long)k * 2 * m > kN)
+        return fail(c, TFHE_B200_ERR_INVALID, "many-function bootstrap: n_functions must be a power of two with n_functions * 2 * message_modulus <= %d", kN);
+    if (!c->has_key || !c->has_ksk) return fail(c, TFHE_B200_ERR_NO_KEY, "no cloud key loaded");
+    if (B == 0) return 0;
+    int shift = 0;
+    while ((1 << shift) < k) shift++;
+    // test vector: position k i + f holds function f's lookup table (lut.Generator.generateLookupTableFull, src/lut/generator.zig:150-191)
+    // at position k i -- a rotation by a multiple of k then leaves function f at every index congruent to f
+    std::vector<uint32_t> tv(2 * kN, 0u), raw(kN), rot(kN);
+    const int offset = (kN + m) / (2 * m);                                 // divRound(N, 2m), generator.zig:253-255
+    for (int f = 0; f < k; f++) {
+        for (int x = 0; x < m; x++) {
+            const int start = (int)(((long long)x * kN + m / 2) / m), end = (int)(((long long)(x + 1) * kN + m / 2) / m);
+            for (int i = start; i < end && i < kN; i++) raw[i] = tables[(size_t)f * m + x];
+        }
+        for (int i = 0; i < kN; i++) rot[i] = raw[(i + offset) % kN];
+        for (int i = kN - offset; i < kN; i++) rot[i] = 0u - rot[i];
+        for (int i = 0; i < kN; i += k) tv[kN + i + f] = rot[i];
+    }
+    const int nd = (int)c->devs.size();
+    if (nd == 1) return many_lut_device(c, c->devs[0], 0, B, B, in, out, tv.data(), k, shift);
+    std::vector<int> rc(nd, 0);
+    std::vector<std::thread> workers;
+    for (int j = 0; j < nd; j++) {
+        const size_t lo = B * j / nd, hi = B * (j + 1) / nd;
+        if (lo == hi) continue;
+        workers.emplace_back([=, &rc, &tv] { rc[j] = many_lut_device(c, c->devs[j], lo, hi, B, in, out, tv.data(), k, shift); });
+    }
+    for (auto &w : workers) w.join();
+    for (int j = 0; j < nd; j++)
+        if (rc[j]) return rc[j];
+    return 0;
 }
 
 int tfhe_b200_lut_generate(tfhe_b200_ctx *c, const uint32_t *table, int message_modulus, uint32_t *testvec_out) {

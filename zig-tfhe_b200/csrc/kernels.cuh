@@ -31,6 +31,7 @@ struct BrArgs {
     int n, L, bgbit;
     uint32_t offset;        // CloudKey.decomposition_offset
     int wide_round;         // 1: F2I.S64 rounding (large-digit sets), 0: magic-add rounding
+    int ms_shift;           // modulus switch to multiples of 2^ms_shift (0: the reference's; > 0: many-function bootstrap)
 #ifdef TFHE_B200_DIAG
     int diag;               // diagnostic builds only (blind_rotate.cu): parts of the kernel switched off
 #endif
@@ -104,6 +105,8 @@ cudaError_t launch_keygen_bsk(const uint32_t *s0, const uint32_t *s1, uint64_t s
 cudaError_t launch_negate(const uint32_t *a, uint32_t *out, size_t count, cudaStream_t s, uint64_t *launches);
 // n_rows trivial ciphertexts (mask 0, body `body`) of w words each: Gates.constant (src/gates.zig:144-151)
 cudaError_t launch_fill_constant(uint32_t *rows, size_t n_rows, int w, uint32_t body, cudaStream_t s, uint64_t *launches);
+// trlwe.sampleExtractIndex(., k) (src/trlwe.zig:146-162) over a batch: [B][2][N] -> [B][N+1]
+cudaError_t launch_sample_extract(const uint32_t *trlwe, uint32_t *lv1, uint32_t B, int k, cudaStream_t s, uint64_t *launches);
 // first n entries + body of an lv1 sample -> TLWELv0-shaped "hybrid" sample (trlwe.zig:165-180)
 cudaError_t launch_extract2(const uint32_t *lv1, uint32_t *out, uint32_t B, int n, cudaStream_t s, uint64_t *launches);
 

@@ -179,6 +179,16 @@ __global__ void fill_constant_kernel(uint32_t *rows, size_t count, int w, uint32
     if (i < count) rows[i] = ((int)(i % (size_t)w) == w - 1) ? body : 0u;
 }
 
+// trlwe.sampleExtractIndex(., k) (src/trlwe.zig:146-162): p[i] = a[k - i] for i <= k, -a[N + k - i] for i > k; p[N] = b[k]
+__global__ void sample_extract_kernel(const uint32_t *trlwe, uint32_t *lv1, uint32_t B, int k) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)B * (kN + 1)) return;
+    const size_t ct = idx / (kN + 1);
+    const int i = (int)(idx - ct * (kN + 1));
+    const uint32_t *a = trlwe + ct * (size_t)(2 * kN), *b = a + kN;
+    lv1[idx] = (i == kN) ? b[k] : (i <= k) ? a[k - i] : 0u - a[kN + k - i];
+}
+
 __global__ void extract2_kernel(const uint32_t *lv1, uint32_t *out, uint32_t B, int n) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t w = (size_t)n + 1;
@@ -242,6 +252,14 @@ cudaError_t launch_fill_constant(uint32_t *rows, size_t n_rows, int w, uint32_t 
     if (!n_rows) return cudaSuccess;
     const size_t count = n_rows * (size_t)w;
     fill_constant_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(rows, count, w, body);
+    if (launches) (*launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sample_extract(const uint32_t *trlwe, uint32_t *lv1, uint32_t B, int k, cudaStream_t s, uint64_t *launches) {
+    if (!B) return cudaSuccess;
+    const size_t total = (size_t)B * (kN + 1);
+    sample_extract_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(trlwe, lv1, B, k);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }

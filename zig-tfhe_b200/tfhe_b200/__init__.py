@@ -102,6 +102,7 @@ def load_library():
         "tfhe_b200_gate_batch_ops": (i32, [vp, vp, vp, vp, vp, sz]),
         "tfhe_b200_bootstrap_batch": (i32, [vp, vp, vp, sz, vp, i32]),
         "tfhe_b200_bootstrap_no_keyswitch_batch": (i32, [vp, vp, vp, sz]),
+        "tfhe_b200_lut_bootstrap_many_batch": (i32, [vp, vp, vp, sz, vp, i32, i32]),
         "tfhe_b200_blind_rotate_batch": (i32, [vp, vp, vp, sz, vp, i32]),
         "tfhe_b200_keyswitch_batch": (i32, [vp, vp, vp, sz]),
         "tfhe_b200_blind_rotate_extract_batch": (i32, [vp, vp, vp, sz]),
@@ -153,6 +154,7 @@ EXPORTED_SYMBOLS = [
     "tfhe_b200_set_tuning", "tfhe_b200_measure_fp64_tflops", "tfhe_b200_last_kernel_ms",
     "tfhe_b200_load_reencryption_key", "tfhe_b200_reencrypt_batch",
     "tfhe_b200_keygen", "tfhe_b200_decomposition_offset", "tfhe_b200_lut_bootstrap_batch", "tfhe_b200_lut_generate",
+    "tfhe_b200_lut_bootstrap_many_batch",
     "tfhe_b200_circuit_create", "tfhe_b200_circuit_destroy", "tfhe_b200_circuit_plan", "tfhe_b200_circuit_info", "tfhe_b200_circuit_run",
     "tfhe_b200_key_file_write", "tfhe_b200_key_file_info", "tfhe_b200_key_file_read", "tfhe_b200_key_file_last_error",
     "tfhe_b200_load_key_file",
@@ -339,6 +341,16 @@ class Context:
         assert tables.shape == ((B, m) if per_item else (m,)), tables.shape
         out = np.empty((B, w), np.uint32)
         self._check(self.lib.tfhe_b200_lut_bootstrap_batch(self.h, _ptr(ct), _ptr(out), B, _ptr(tables), m, 1 if per_item else 0))
+        return out
+
+    def lut_bootstrap_many_batch(self, ct, tables):
+        """several functions from one blind rotation: tables [k][m] torus values (k a power of two, k * 2m <= N) -> [k][B][n+1]"""
+        w = self.n + 1
+        ct = _u32(ct, w); B = ct.shape[0]
+        tables = np.ascontiguousarray(tables, dtype=np.uint32)
+        k, m = tables.shape
+        out = np.empty((k, B, w), np.uint32)
+        self._check(self.lib.tfhe_b200_lut_bootstrap_many_batch(self.h, _ptr(ct), _ptr(out), B, _ptr(tables), k, m))
         return out
 
     def lut_generate(self, table):
