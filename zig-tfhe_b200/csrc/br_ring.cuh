@@ -60,6 +60,13 @@ __device__ __forceinline__ void ring_release(Producer &pr, int stage, uint32_t c
     }
 }
 
+// (Key chunks through TENSOR memory instead of shared memory for the pointwise MAC -- bulk copy into a shared-memory stage,
+// sixteen tcgen05.cp.64x128b.warpx2::02_13 per chunk into 64 tensor-memory columns, tcgen05.ld.x16 by every thread from its
+// own lane, a second three-stage ring with its own last-arriver protocol -- was built and measured at six ciphertexts per
+// CTA: bit-exact, 22 % fewer shared-memory wavefronts, and 76.2 k instead of 103.3 k bootstraps/s.  tcgen05.ld delivers
+// ~64-100 B/clk/SM; with the twiddles already coming from tensor memory the key reads (576 KB per SM and step on top of
+// 786 KB) saturate it.  Removed again; profiles/r02_k1_ring.log.)
+
 // Per-group exchange state.  X2 is double-buffered when DBX2 (one named barrier per transform instead
 // of two): a writer of buffer b at transform k has passed the barrier of transform k-1, which every
 // reader of b at transform k-2 reached only after finishing its reads.
