@@ -122,6 +122,9 @@ __device__ __forceinline__ void x1_shuffle(cplx (&v)[8], int lo) {   // new v[q]
     x1_shuffle_stage<1>(v, (lo & 1) != 0);
 }
 
+// (X1 WITHOUT shared memory -- the 8 x 8 transpose between the eight lanes of an octet and their registers as three butterfly
+// stages of warp shuffles, 48 SHFL + 96 SEL per thread instead of 8 STS.128 + 8 LDS.128 -- was built and measured at six
+// ciphertexts per CTA: bit-exact, 89.1 k instead of 103.0 k bootstraps/s.  Removed again; profiles/r02_k1_ring.log.)
 // ALIAS: X1 lives in the X2 buffer this transform does NOT use for its own X2 exchange (rows of this warp only), see
 // Layout::kX1Alias for why that is race-free.
 template <bool USE_TMA, bool DBX2, int POW, int POW3, bool ALIAS = false, bool X1S = false>
