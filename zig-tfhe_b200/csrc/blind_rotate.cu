@@ -100,40 +100,17 @@ struct Tw2 {
 };
 
 // forward transform, role A registers in -> role C (leaf order) out
-// X1 without shared memory: the 8 x 8 transpose between the eight lanes of an octet and their eight registers as three
-// butterfly stages of warp shuffles (lane bit m <-> register bit m): 48 SHFL + 96 SEL per thread instead of 8 STS.128 +
-// 8 LDS.128 -- trades issue slots (49 % busy) for shared-memory wavefronts (82 % busy).  Tuning key "twt" = 3.
-template <int M>
-__device__ __forceinline__ void x1_shuffle_stage(cplx (&v)[8], bool p) {
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-        if (r & M) continue;
-        const cplx send = p ? v[r] : v[r | M];
-        cplx recv;
-        recv.re = __shfl_xor_sync(0xffffffffu, send.re, M);
-        recv.im = __shfl_xor_sync(0xffffffffu, send.im, M);
-        if (p) v[r] = recv;
-        else v[r | M] = recv;
-    }
-}
-__device__ __forceinline__ void x1_shuffle(cplx (&v)[8], int lo) {   // new v[q] of lane lo = old v[lo] of lane q (same octet)
-    x1_shuffle_stage<4>(v, (lo & 4) != 0);
-    x1_shuffle_stage<2>(v, (lo & 2) != 0);
-    x1_shuffle_stage<1>(v, (lo & 1) != 0);
-}
-
 // (X1 WITHOUT shared memory -- the 8 x 8 transpose between the eight lanes of an octet and their registers as three butterfly
 // stages of warp shuffles, 48 SHFL + 96 SEL per thread instead of 8 STS.128 + 8 LDS.128 -- was built and measured at six
 // ciphertexts per CTA: bit-exact, 89.1 k instead of 103.0 k bootstraps/s.  Removed again; profiles/r02_k1_ring.log.)
 // ALIAS: X1 lives in the X2 buffer this transform does NOT use for its own X2 exchange (rows of this warp only), see
 // Layout::kX1Alias for why that is race-free.
-template <bool USE_TMA, bool DBX2, int POW, int POW3, bool ALIAS = false, bool X1S = false>
+template <bool USE_TMA, bool DBX2, int POW, int POW3, bool ALIAS = false>
 __device__ __forceinline__ void fwd_transform(cplx (&v)[8], Xbuf &xb, const Tw2<POW> &tw2, const Tw2<POW3> &tw3, int hi, int lo,
                                               int barid, Producer &pr, int nthr = kGroupThreads, int diag = 0) {
     fwd_pass1(v);
     cplx *x1 = ALIAS ? xb.x2 + (xb.flip ^ kX2Slots) : xb.x1;
-    if (X1S) x1_shuffle(v, lo);
-    else if (!(diag & 8)) {
+    if (!(diag & 8)) {
 #pragma unroll
     for (int q = 0; q < 8; q++) x1[ALIAS ? x1a_slot(hi, q, lo) : x1_slot(hi, q, lo)] = v[q];
     __syncwarp();
@@ -164,7 +141,7 @@ __device__ __forceinline__ void fwd_transform(cplx (&v)[8], Xbuf &xb, const Tw2<
 }
 
 // inverse transform, role C (leaf order) in -> role A out: v[p] = c_e, e = 64 p + 8 lo + hi
-template <bool USE_TMA, bool DBX2, int POW, int POW3, bool ALIAS = false, bool X1S = false>
+template <bool USE_TMA, bool DBX2, int POW, int POW3, bool ALIAS = false>
 __device__ __forceinline__ void inv_transform(cplx (&v)[8], Xbuf &xb, const Tw2<POW> &tw2, const Tw2<POW3> &tw3, int hi, int lo,
                                               int barid, Producer &pr, int nthr = kGroupThreads, int diag = 0) {
     {
@@ -191,8 +168,6 @@ __device__ __forceinline__ void inv_transform(cplx (&v)[8], Xbuf &xb, const Tw2<
     // ALIAS: the inverse X2 reads cross both warps' rows, so X1 may reuse that same buffer (this warp's rows) only once
     // every thread of the group has finished them: one more group barrier, on two of the eight transforms of a step
     cplx *x1 = ALIAS ? x2 : xb.x1;
-    if (X1S) x1_shuffle(v, lo);
-    else {
     if (ALIAS) bar_sync(barid, nthr);
     if (!(diag & 8)) {
 #pragma unroll
@@ -200,7 +175,6 @@ __device__ __forceinline__ void inv_transform(cplx (&v)[8], Xbuf &xb, const Tw2<
     __syncwarp();
 #pragma unroll
     for (int q = 0; q < 8; q++) v[q] = x1[ALIAS ? x1a_slot(hi, q, lo) : x1_slot(hi, q, lo)];
-    }
     }
     inv_pass1(v);
 }
@@ -283,7 +257,6 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
     using Lay = Layout<KCT, TEAM, (TWT != 0 && KCT > 4)>;
     static_assert(TWT == 0 || TEAM == 1 || KCT > 4, "teams of two with tensor-memory twiddles: six ciphertexts per CTA only");
     constexpr bool XA = Lay::kX1Alias;
-    constexpr bool X1S = TWT == 3;                 // X1 through warp shuffles
     constexpr bool TWT_ON = TWT != 0;              // both twiddle sets in tensor memory, accumulators in registers
     constexpr int POW = TWT_ON ? kTwTmem : Lay::kTw2Mode, POW3 = TWT_ON ? kTwTmem : Lay::kTw3Mode;
     constexpr bool DBX2 = Lay::kDbX2;
@@ -487,7 +460,7 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
                 for (int l = 0; l < L; l++) {
                     cplx v[8];
                     digits_to_cplx(v, d, 32 - (l + 1) * bgbit, mask, half_bg);
-                    fwd_transform<USE_TMA, DBX2, POW, POW3, XA, X1S>(v, xb, tw2, tw3, hi, lo, barid, pr, kTeamThreads, diag);
+                    fwd_transform<USE_TMA, DBX2, POW, POW3, XA>(v, xb, tw2, tw3, hi, lo, barid, pr, kTeamThreads, diag);
                     const cplx *chunk;
                     if (USE_TMA) {
                         if (!DIAG_ON(P, 0) && !DIAG_ON(P, 5)) {
@@ -522,9 +495,9 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
                     }
                 }
             }
-            inv_transform<USE_TMA, DBX2, POW, POW3, XA, X1S>(oa, xb, tw2, tw3, hi, lo, barid, pr, kTeamThreads, diag);
+            inv_transform<USE_TMA, DBX2, POW, POW3, XA>(oa, xb, tw2, tw3, hi, lo, barid, pr, kTeamThreads, diag);
             round_accumulate<MARGIN>(oa, acc_a, t, wide, margin);
-            inv_transform<USE_TMA, DBX2, POW, POW3, XA, X1S>(ob, xb, tw2, tw3, hi, lo, barid, pr, kTeamThreads, diag);
+            inv_transform<USE_TMA, DBX2, POW, POW3, XA>(ob, xb, tw2, tw3, hi, lo, barid, pr, kTeamThreads, diag);
             round_accumulate<MARGIN>(ob, acc_b, t, wide, margin);
         } else {
             // ---- accumulators in TMEM (168-register budget): each half is loaded, updated and stored back
@@ -961,12 +934,12 @@ cudaError_t launch_latency(const BrArgs &a, cudaStream_t s) {
 }
 
 // tensor-memory twiddles (tuning key "twt"): throughput kernel at KCT = 4, 5, 6, TMA ring, no margin tracking
-template <int KCT, int TEAM = 1, int TWT = 1>
+template <int KCT, int TEAM = 1>
 cudaError_t launch_twt(const BrArgs &a, cudaStream_t s) {
     using Lay = Layout<KCT, TEAM, (KCT > 4)>;
     const size_t smem = Lay::kStages * kBskChunkBytes + 96 + (size_t)KCT * Lay::group_bytes(a.n);
-    auto kern = blind_rotate_kernel<KCT, true, false, TEAM, 0, TWT>;
-    if (a.L == 3 && a.bgbit == 6 && !a.wide_round) kern = blind_rotate_kernel<KCT, true, false, TEAM, 3, TWT>;
+    auto kern = blind_rotate_kernel<KCT, true, false, TEAM, 0, 1>;
+    if (a.L == 3 && a.bgbit == 6 && !a.wide_round) kern = blind_rotate_kernel<KCT, true, false, TEAM, 3, 1>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<(a.B + KCT - 1) / KCT, KCT * kGroupThreads, smem, s>>>(a);
@@ -1070,7 +1043,6 @@ cudaError_t launch_blind_rotate(const BrArgs &a, const BrTuning &tune, bool trac
     // tensor-memory twiddles: the KCT = 6 default, or forced (tuning key "twt" = 1) at 4 and 5
     // (teams of two on top of it -- launch_twt<6, 2>, key loads of two ciphertexts merged -- measured 102.7 k against 103.3 k/s:
     // not instantiated)
-    if (twt_ok && kct == 6 && tune.twt == 3) return launch_twt<6, 1, 3>(a, s);
     if (twt_ok && (kct == 6 || (tune.twt > 0 && kct >= 4)))
         return kct == 4 ? launch_twt<4>(a, s) : kct == 5 ? launch_twt<5>(a, s) : launch_twt<6>(a, s);
     if (tune.use_tma != 0 && (kct == 2 || kct == 4 || kct == 6) && tune.team == 2)
