@@ -602,6 +602,9 @@ int tfhe_b200_load_key(tfhe_b200_ctx *c, const double *bsk, const uint32_t *ksk,
     }
     for (Device &d : c->devs)
         if (int r = upload_key_device(c, d, bsk, false, ksk, false, stride)) {
+            // some devices now hold the new key and some the previous one: a batch sharded over them would mix keys, so the
+            // context has no key until a load succeeds on every device
+            for (Device &e : c->devs) e.has_key = e.has_ksk = false;
             refresh_key_flags(c);
             return r;
         }
