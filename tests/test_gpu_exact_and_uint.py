@@ -134,9 +134,11 @@ def test_exact_register_blocked_equals_legacy_and_oracle(name, modulus):
         legacy = c.blind_rotate_batch(ct, tv)
         c.set_tuning("exact_legacy", 0)
         assert (got == legacy).all()
-        for kct in (1, 2, 3, 4):
+        for kct in (1, 2, 3, 4, 6):      # 6: tensor-memory twiddles, X1 over X2, last-arriver ring
             c.set_tuning("exact_kct", kct)
             assert (c.blind_rotate_batch(ct[:23], tv) == got[:23]).all(), kct
+        c.set_tuning("exact_kct", 4)
+        assert (c.blind_rotate_batch(ct, tv) == got).all()      # the 601-item batch on the four-per-CTA kernel (default here: < 888)
         c.set_tuning("exact_kct", 0)
         c.track_margin(True)
         assert (c.blind_rotate_batch(ct[:9], tv) == got[:9]).all()

@@ -190,21 +190,58 @@ struct ExactConsts {
                                      // parameters live in the constant bank, so they cost no registers)
 };
 
-template <bool CONJ, bool USE_TMA>
-__device__ __forceinline__ void ex_transform(cplx (&v)[8], Xbuf &xb, const ExTw &twb, const ExTw &twc, const ExactConsts &kc, int hi, int lo,
-                                             int barid, Producer &pr) {
+// Per-thread stage twiddles of passes B and C: resident in registers (2 x 28), or -- DENSE, six ciphertexts per CTA at 168
+// registers -- parked in 64 tensor-memory columns of the thread's own lane and fetched by one tcgen05.ld before each pass
+// (same scheme as the fast kernel's "twt", blind_rotate.cu).
+template <bool DENSE>
+struct ExTwSrc {
+    ExTw b, c;            // !DENSE
+    uint32_t taddr;       // DENSE: pass B in columns [0, 32), pass C in [32, 64)
+    __device__ __forceinline__ ExTw get(int which) const {
+        if (!DENSE) return which ? c : b;
+        uint32_t r[32];
+        tmem_ld32(taddr + 32u * (uint32_t)which, r);
+        tmem_wait_ld();
+        ExTw w;
+        auto cp = [&](int k) { return cplx{__hiloint2double((int)r[4 * k + 1], (int)r[4 * k]), __hiloint2double((int)r[4 * k + 3], (int)r[4 * k + 2])}; };
+        w.wa = cp(0); w.wb[0] = cp(1); w.wb[1] = cp(2); w.wc[0] = cp(3); w.wc[1] = cp(4); w.wc[2] = cp(5); w.wc[3] = cp(6);
+        return w;
+    }
+};
+__device__ __forceinline__ void ex_tw_park(uint32_t taddr, const ExTw &w) {
+    uint32_t r[32];
+    const cplx v[7] = {w.wa, w.wb[0], w.wb[1], w.wc[0], w.wc[1], w.wc[2], w.wc[3]};
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+        r[4 * k] = (uint32_t)__double2loint(v[k].re); r[4 * k + 1] = (uint32_t)__double2hiint(v[k].re);
+        r[4 * k + 2] = (uint32_t)__double2loint(v[k].im); r[4 * k + 3] = (uint32_t)__double2hiint(v[k].im);
+    }
+#pragma unroll
+    for (int k = 28; k < 32; k++) r[k] = 0u;
+    tmem_st32(taddr, r);
+}
+
+// DENSE also lays X1 over this warp's rows of the X2 buffer the transform does not use for its own X2 exchange (x1a_slot):
+// every exact transform runs A -> X1 -> B -> X2 -> C, its X2 reads are partitioned by warp, and the other warp writes that
+// buffer again only one transform later, after the group barrier this warp reaches with X1 long finished.
+template <bool CONJ, bool DENSE>
+__device__ __forceinline__ void ex_transform(cplx (&v)[8], Xbuf &xb, const ExTwSrc<DENSE> &tw, const ExactConsts &kc, int hi, int lo, int barid,
+                                             Producer &pr) {
     {
         const cplx twa[kExactPassATw] = {cplx{1.0, 0.0}, cplx{1.0, 0.0}, kc.twa2, cplx{1.0, 0.0}, kc.twa4, kc.twa5, kc.twa6};
         ex_pass_a<CONJ>(v, twa);
     }
-    cplx *x1 = xb.x1;
+    cplx *x1 = DENSE ? xb.x2 + (xb.flip ^ kX2Slots) : xb.x1;
 #pragma unroll
-    for (int q = 0; q < 8; q++) x1[x1_slot(hi, q, lo)] = v[q];
+    for (int q = 0; q < 8; q++) x1[DENSE ? x1a_slot(hi, q, lo) : x1_slot(hi, q, lo)] = v[q];
     __syncwarp();
 #pragma unroll
-    for (int q = 0; q < 8; q++) v[q] = x1[x1_slot(hi, lo, q)];
-    ex_pass<CONJ>(v, twb.wa, twb.wb, twb.wc);
-    if (USE_TMA) producer_poll(pr);
+    for (int q = 0; q < 8; q++) v[q] = x1[DENSE ? x1a_slot(hi, lo, q) : x1_slot(hi, lo, q)];
+    {
+        const ExTw w = tw.get(0);
+        ex_pass<CONJ>(v, w.wa, w.wb, w.wc);
+    }
+    if (!DENSE) producer_poll(pr);
     cplx *x2 = xb.x2 + xb.flip;      // double-buffered: one named barrier per transform (see Xbuf)
     xb.flip ^= kX2Slots;
 #pragma unroll
@@ -212,12 +249,15 @@ __device__ __forceinline__ void ex_transform(cplx (&v)[8], Xbuf &xb, const ExTw 
     bar_sync(barid, kGroupThreads);
 #pragma unroll
     for (int q = 0; q < 8; q++) v[q] = x2[x2_slot(hi, lo, q)];
-    ex_pass<CONJ>(v, twc.wa, twc.wb, twc.wc);
+    {
+        const ExTw w = tw.get(1);
+        ex_pass<CONJ>(v, w.wa, w.wb, w.wc);
+    }
 }
 
 constexpr int kExStages = 3;
-__host__ __device__ constexpr int ex_group_bytes(int n) { return 2 * kN * 4 + kX1Slots * 16 + 2 * kX2Slots * 16 + align16((n + 1) * 2); }
-__host__ __device__ constexpr int ex_fixed_bytes() { return kExStages * kBskChunkBytes + 80 + kExactSharedTabCplx * 16; }
+__host__ __device__ constexpr int ex_group_bytes(int n, bool dense) { return 2 * kN * 4 + (dense ? 0 : kX1Slots * 16) + 2 * kX2Slots * 16 + align16((n + 1) * 2); }
+__host__ __device__ constexpr int ex_fixed_bytes() { return kExStages * kBskChunkBytes + 112 + kExactSharedTabCplx * 16; }
 
 template <int KCT, bool MARGIN>
 __global__ void __launch_bounds__(KCT * kGroupThreads, 1)
@@ -227,9 +267,12 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1)
     unsigned char *ptr = smem_raw;
     cplx *bsk_ring = reinterpret_cast<cplx *>(ptr);
     ptr += kExStages * kBskChunkBytes;
+    constexpr bool DENSE = KCT > 4;      // six ciphertexts per CTA: tensor-memory twiddles, X1 over X2, last-arriver key ring
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(ptr);
     uint64_t *empty_bar = full_bar + kMaxStages;
-    ptr += 80;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(ptr + 64);
+    uint32_t *ring_cnt = reinterpret_cast<uint32_t *>(ptr + 80);   // [kMaxStages] releases per stage (last-arriver refill)
+    ptr += 112;
     cplx *twist = reinterpret_cast<cplx *>(ptr);     // [512] in acc_pos order
     ptr += kExactSharedTabCplx * 16;
     const int n = P.n, L = P.L, bgbit = P.bgbit;
@@ -240,28 +283,47 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1)
         for (int s = 0; s < kExStages; s++) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], n_active * 2);   // one arrival per consumer warp
+            ring_cnt[s] = 0u;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    if (DENSE && tid < 32) {
+        tmem_alloc(tmem_slot, 256);     // 64 columns per warp, three warps per lane quadrant
+        tmem_fence_before_sync();
+    }
     for (int j = tid; j < kExactSharedTabCplx; j += KCT * kGroupThreads) twist[j] = shared_tab[j];
     __syncthreads();
+    uint32_t tmem_base = 0;
+    if (DENSE) {
+        tmem_fence_after_sync();
+        tmem_base = *tmem_slot;
+    }
     const int g = tid >> 6, t = tid & 63;
-    if (g >= n_active) return;     // whole warps
+    if (g >= n_active) return;     // whole warps (warp 0 is always active: it frees the tensor-memory allocation at the end)
     const int hi = t >> 3, lo = t & 7;
     const int barid = 1 + g;
-    unsigned char *gb = ptr + (size_t)g * ex_group_bytes(n);
+    unsigned char *gb = ptr + (size_t)g * ex_group_bytes(n, DENSE);
     uint32_t *acc_a = reinterpret_cast<uint32_t *>(gb), *acc_b = acc_a + kN;
+    constexpr int kX1B = DENSE ? 0 : kX1Slots * 16;
     Xbuf xb;
     xb.x1 = reinterpret_cast<cplx *>(gb + 2 * kN * 4);
-    xb.x2 = xb.x1 + kX1Slots;
+    xb.x2 = reinterpret_cast<cplx *>(gb + 2 * kN * 4 + kX1B);
     xb.flip = 0;
-    uint16_t *atil = reinterpret_cast<uint16_t *>(gb + 2 * kN * 4 + kX1Slots * 16 + 2 * kX2Slots * 16);
+    uint16_t *atil = reinterpret_cast<uint16_t *>(gb + 2 * kN * 4 + kX1B + 2 * kX2Slots * 16);
     const size_t ct = (size_t)P.ct_base + first_ct + g;
 
     // per-thread stage twiddles (forward table; the inverse direction uses their exact conjugates)
-    const ExTw twb = ex_twiddles_b(tables + 2 * kExactTabStride, tables + 3 * kExactTabStride, lo);
-    const ExTw twc = ex_twiddles_c(tables + 2 * kExactTabStride, tables + 3 * kExactTabStride, 8 * lo + hi);
+    ExTwSrc<DENSE> tw;
+    if (DENSE) {
+        tw.taddr = tmem_base + ((uint32_t)((tid >> 5) & 3) << 21) + (uint32_t)(tid >> 7) * 64u;
+        ex_tw_park(tw.taddr, ex_twiddles_b(tables + 2 * kExactTabStride, tables + 3 * kExactTabStride, lo));
+        ex_tw_park(tw.taddr + 32u, ex_twiddles_c(tables + 2 * kExactTabStride, tables + 3 * kExactTabStride, 8 * lo + hi));
+        tmem_wait_st();
+    } else {
+        tw.b = ex_twiddles_b(tables + 2 * kExactTabStride, tables + 3 * kExactTabStride, lo);
+        tw.c = ex_twiddles_c(tables + 2 * kExactTabStride, tables + 3 * kExactTabStride, 8 * lo + hi);
+    }
 
     {   // gate linear part (gates.zig:48-121) + modulus switch (trgsw.zig:297,312)
         const GateOperands go = gate_operands(P, ct, n);
@@ -293,12 +355,25 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1)
     uint32_t phase = 0;
     double margin = 0.0;
     Producer pr;
-    pr.src = bsk_x; pr.ring = bsk_ring; pr.full_bar = full_bar; pr.empty_bar = empty_bar;
-    pr.remaining = n * 2 * L; pr.issued = 0; pr.stage = 0; pr.phase = 0; pr.stages = kExStages;
-    pr.active = tid == 0;
-    pr.policy = pr.active ? l2_policy_evict_last() : 0;
+    pr.ring = bsk_ring; pr.full_bar = full_bar; pr.empty_bar = empty_bar; pr.stages = kExStages;
+    pr.ring_cnt = ring_cnt; pr.bsk = bsk_x; pr.total = (uint32_t)(n * 2 * L); pr.ring_warps = (uint32_t)(n_active * 2);
+    if (DENSE) {     // last-arriver refill (br_ring.cuh): thread 0 fills the ring once, the consumers issue every later bulk copy
+        pr.active = false; pr.remaining = 0;
+        if (tid == 0) {
+            const uint64_t policy = l2_policy_evict_last();
+            for (int s = 0; s < kExStages && s < n * 2 * L; s++) {
+                mbar_arrive_expect_tx(&full_bar[s], kBskChunkBytes);
+                bulk_g2s(bsk_ring + s * kBskChunkCplx, bsk_x + (size_t)s * kBskChunkCplx, kBskChunkBytes, &full_bar[s], policy);
+            }
+        }
+    } else {
+        pr.src = bsk_x;
+        pr.remaining = n * 2 * L; pr.issued = 0; pr.stage = 0; pr.phase = 0;
+        pr.active = tid == 0;
+        pr.policy = pr.active ? l2_policy_evict_last() : 0;
 #pragma unroll
-    for (int s = 0; s < kExStages; s++) producer_poll(pr);
+        for (int s = 0; s < kExStages; s++) producer_poll(pr);
+    }
     __nanosleep((blockIdx.x % 41u) * 128u);   // de-synchronise the CTAs of a wave (see blind_rotate.cu)
 
     for (int i = 0; i < n; i++) {
@@ -321,16 +396,21 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1)
                     const double x_im = (double)(int32_t)(((d[2 * p + 1] >> sh) & mask) - half_bg);
                     v[p] = ex_twist(x_re, x_im, twist[64 * p + t]);
                 }
-                ex_transform<false, true>(v, xb, twb, twc, kc, hi, lo, barid, pr);
-                while (!mbar_try_wait(&full_bar[stage], phase)) producer_poll(pr);
+                ex_transform<false, DENSE>(v, xb, tw, kc, hi, lo, barid, pr);
+                if (DENSE) mbar_wait(&full_bar[stage], phase);
+                else
+                    while (!mbar_try_wait(&full_bar[stage], phase)) producer_poll(pr);
                 const cplx *chunk = bsk_ring + stage * kBskChunkCplx;
 #pragma unroll
                 for (int q = 0; q < 8; q++) {
                     ex_mac(oa[q], v[q], chunk[bsk_slot(0, q, t)]);
                     ex_mac(ob[q], v[q], chunk[bsk_slot(1, q, t)]);
                 }
-                __syncwarp();
-                if ((tid & 31) == 0) mbar_arrive(&empty_bar[stage]);
+                if (DENSE) ring_release(pr, stage, (uint32_t)((i * 2 + h) * L + l), tid & 31);
+                else {
+                    __syncwarp();
+                    if ((tid & 31) == 0) mbar_arrive(&empty_bar[stage]);
+                }
                 if (++stage == kExStages) { stage = 0; phase ^= 1; }
             }
         }
@@ -341,7 +421,7 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1)
 #pragma unroll
                 for (int q = 0; q < 8; q++) oa[q] = ob[q];
             }
-            ex_transform<true, true>(oa, xb, twb, twc, kc, hi, lo, barid, pr);
+            ex_transform<true, DENSE>(oa, xb, tw, kc, hi, lo, barid, pr);
 #pragma unroll
             for (int p = 0; p < 8; p++) {
                 const cplx r = ex_untwist(oa[p], twist[64 * p + t]);
@@ -369,11 +449,19 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1)
         for (int s = 16; s > 0; s >>= 1) margin = fmax(margin, __shfl_xor_sync(0xffffffffu, margin, s));
         if ((tid & 31) == 0) atomicMax(P.margin_bits, (unsigned long long)__double_as_longlong(margin));
     }
+    if (DENSE) {
+        tmem_fence_before_sync();
+        bar_sync(15, n_active * kGroupThreads);      // every active warp is done with its tensor-memory window
+        if (tid < 32) {
+            tmem_fence_after_sync();
+            tmem_dealloc(tmem_base, 256);
+        }
+    }
 }
 
 template <int KCT>
 cudaError_t launch_rb(const BrArgs &a, const ExactArgs &x, const ExactConsts &kc, bool margin, cudaStream_t s) {
-    const size_t smem = ex_fixed_bytes() + (size_t)KCT * ex_group_bytes(a.n);
+    const size_t smem = ex_fixed_bytes() + (size_t)KCT * ex_group_bytes(a.n, KCT > 4);
     auto k0 = blind_rotate_exact_rb_kernel<KCT, false>;
     auto k1 = blind_rotate_exact_rb_kernel<KCT, true>;
     cudaError_t e = cudaFuncSetAttribute(margin ? k1 : k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -399,16 +487,22 @@ cudaError_t launch_blind_rotate_exact(const BrArgs &a, const ExactArgs &x, bool 
         }();
         const unsigned sms = x.sm_count > 0 ? (unsigned)x.sm_count : 148u;
         int kct = x.kct;
-        if (kct < 1 || kct > 4) {      // fewest CTA waves; below one wave, the narrowest CTA that still covers the batch
-            kct = 4;
-            for (int k = 1; k <= 4; k++)
-                if ((a.B + sms * k - 1) / (sms * k) <= (a.B + sms * 4 - 1) / (sms * 4)) { kct = k; break; }
+        if (kct < 1 || kct > 6 || kct == 5) {
+            // six ciphertexts per CTA (tensor-memory twiddles, profiles/r02_k1x_dense.log) from one full wave of them up, unless
+            // margin tracking is on; else the fewest waves of up to four, and below one wave the narrowest CTA that covers the batch
+            if (a.B >= sms * 6 && !track_margin && a.n <= 1024) kct = 6;
+            else {
+                kct = 4;
+                for (int k = 1; k <= 4; k++)
+                    if ((a.B + sms * k - 1) / (sms * k) <= (a.B + sms * 4 - 1) / (sms * 4)) { kct = k; break; }
+            }
         }
         if (launches) (*launches)++;
         switch (kct) {
             case 1: return launch_rb<1>(a, x, kc, track_margin, s);
             case 2: return launch_rb<2>(a, x, kc, track_margin, s);
             case 3: return launch_rb<3>(a, x, kc, track_margin, s);
+            case 6: return launch_rb<6>(a, x, kc, track_margin, s);
             default: return launch_rb<4>(a, x, kc, track_margin, s);
         }
     }
