@@ -27,11 +27,15 @@ ca = orc.encrypt_bools(pa, keys, 101); cb = orc.encrypt_bools(pb, keys, 102)
 t0 = time.time()
 checked = 0
 for r in range(rounds):
-    B = int(rng.choice([1, 2, 3, 37, 74, 75, 100, 148, 149, 300, 591, 592, 593, 700, 1185, 2048, int(rng.integers(1, 2500))]))
+    B = int(rng.choice([1, 2, 3, 37, 74, 75, 100, 148, 149, 300, 591, 592, 593, 700, 1185, 888, 889, 2048, int(rng.integers(1, 2500))]))
     idx = rng.integers(0, pool, B)
     ops = rng.integers(0, 10, B).astype(np.int32)
     ctx.set_tuning("latency_mode", int(rng.choice([0, 1, 1, 2])))
-    ctx.set_tuning("kct", int(rng.choice([0, 0, 0, 1, 2, 3, 4])))
+    ctx.set_tuning("kct", int(rng.choice([0, 0, 0, 1, 2, 3, 4, 6])))
+    ctx.set_tuning("twt", int(rng.choice([0, 0, -1, 1])))              # tensor-memory twiddles: where they win / never / also at 4 and 5
+    ctx.set_tuning("ks_tc", int(rng.choice([0, 0, -1, 1])))            # key switch: automatic / scalar kernel / tensor cores
+    ctx.set_mode(tfhe_b200.MODE_EXACT if rng.integers(0, 6) == 0 else tfhe_b200.MODE_FAST)
+    ctx.set_tuning("exact_kct", int(rng.choice([0, 0, 4, 6])))
     out = ctx.gate_batch(ops, ca[idx], cb[idx])
     want = np.array([TRUTH[int(ops[i])](int(pa[idx[i]]), int(pb[idx[i]])) for i in range(B)], np.uint8)
     got = orc.decrypt_bools(out, keys)

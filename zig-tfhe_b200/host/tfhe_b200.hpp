@@ -92,6 +92,17 @@ public:
         check(tfhe_b200_lut_bootstrap_batch(ctx_, c.data(), out.data(), 1, table.data(), (int)table.size(), 0));
         return out;
     }
+    // several functions from ONE blind rotation: tables[f][x], f < tables.size() (a power of two), returns one ciphertext per function
+    std::vector<Ciphertext> bootstrapLutMany(const Ciphertext &c, const std::vector<std::vector<uint32_t>> &tables) const {
+        const size_t k = tables.size(), m = k ? tables[0].size() : 0;
+        std::vector<uint32_t> flat;
+        for (const auto &t : tables) flat.insert(flat.end(), t.begin(), t.end());
+        std::vector<uint32_t> out(k * (size_t)words_);
+        check(tfhe_b200_lut_bootstrap_many_batch(ctx_, c.data(), out.data(), 1, flat.data(), (int)k, (int)m));
+        std::vector<Ciphertext> res;
+        for (size_t f = 0; f < k; f++) res.emplace_back(out.begin() + f * words_, out.begin() + (f + 1) * words_);
+        return res;
+    }
     const char *name() const { return "b200"; }
     tfhe_b200_ctx *ctx() const { return ctx_; }
     int words() const { return words_; }
@@ -176,6 +187,7 @@ inline auto batchXnor(const GpuBootstrap &b, const std::vector<std::pair<Ciphert
 class Circuit {
 public:
     static constexpr uint32_t kNot = TFHE_B200_WIRE_NOT;
+    static constexpr uint32_t kTrue = TFHE_B200_WIRE_TRUE, kFalse = TFHE_B200_WIRE_FALSE;   // Gates.constant wires (gates.zig:144-151)
     Circuit(const GpuBootstrap &b, const std::vector<tfhe_b200_gate_node> &gates, size_t n_inputs, const std::vector<uint32_t> &outputs)
         : b_(b), n_inputs_(n_inputs), n_outputs_(outputs.size()) {
         b_.check(tfhe_b200_circuit_create(b_.ctx(), gates.data(), gates.size(), n_inputs, outputs.data(), outputs.size(), &c_));
