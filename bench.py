@@ -432,7 +432,7 @@ def main():
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         sm_mhz = clocks.get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
         arith_peak = 148 * 64 * 2 * sm_mhz * 1e6 / 1e12      # 64 FP64 FMA lanes per SM per clock
-        kct = args.kct or 4
+        kct = args.kct or 6      # six ciphertexts per CTA is the full-wave configuration (blind_rotate.cu)
         waves = -(-B // (148 * kct))
         io_bytes = B * ((1 if is_lut else 2) * w * 4 + 4 + 4100)      # operands + opcode in, one lv1 sample out
         traffic, traffic_src = None, None                  # dram bytes per launch of K1 from the committed ncu capture
