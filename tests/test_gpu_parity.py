@@ -270,12 +270,13 @@ def test_split_launch_full_waves_plus_tail(ctx128, orc128, keys128):
         assert (got[i] == orc128.blind_rotate_batch(ca[i:i + 1], keys128, tv[i])[0]).all(), i
 
 
-@pytest.mark.parametrize("name", ["128", "80", "110", "uint1"])
+@pytest.mark.parametrize("name", ["128", "80", "110", "uint1", "uint2", "uint4"])
 def test_tensor_core_keyswitch_bit_exact(name):
     """K2t (keyswitch_tc.cu): the key switch as a u8 x u8 -> s32 tcgen05 contraction over one-hot digits, four byte
     planes recombined mod 2^32 -- integer arithmetic, so the bar is equality with trgsw.identityKeySwitching
     (src/trgsw.zig:471-502) on every word, at row counts around the 128-row MMA tile and for every column-group width
-    (n + 1 = 551, 631, 701: last groups of 40, 120 and 64 columns)."""
+    (n + 1 = 551, 631, 701: last groups of 40, 120 and 64 columns), and on the BASEBIT = 4 / 5 sets (UINT2 / UINT4: 2^BASEBIT one-hot
+    bytes per digit, 6 / 3 digits per 96-byte K block)."""
     import tfhe_b200
     orc = O.Oracle(name); k = keys_for(name)
     c = tfhe_b200.Context(name, devices=[0])
@@ -294,7 +295,7 @@ def test_tensor_core_keyswitch_bit_exact(name):
         assert (c.keyswitch_batch(lv1) == ref).all()          # scalar kernel, same bits
         c.set_tuning("ks_tc", 0)
         # whole gates through K1 -> K2t (automatic selection from 192 ciphertexts up); uint1's transform is exact only in exact mode
-        if name == "uint1":
+        if name.startswith("uint"):
             c.set_mode(tfhe_b200.MODE_EXACT)
         bits = rng.integers(0, 2, 300).astype(np.uint8)
         ca = orc.encrypt_bools(bits, k, 1); cb = orc.encrypt_bools(1 - bits, k, 2)

@@ -139,7 +139,7 @@ int run_keyswitch(tfhe_b200_ctx *c, Device &d, const uint32_t *lv1, uint32_t *lv
     const bool tc = d.ksk_tc && c->ks_tc >= 0 && (c->ks_tc > 0 || B >= (size_t)c->ks_tc_min);
     if (tc) {
         if (!ks_digits) {
-            if (int r = ensure(c, d.ksdig, B * keyswitch_tc_digit_words(c->prm.iks_t) * 8)) return r;
+            if (int r = ensure(c, d.ksdig, B * keyswitch_tc_digit_words(c->prm.basebit, c->prm.iks_t) * 8)) return r;
             ks_digits = (uint64_t *)d.ksdig.p;
         }
         CU(c, launch_keyswitch_tc(K, d.ksk_tc, ks_digits, d.stream, launches));
@@ -363,8 +363,8 @@ int build_tc_key(tfhe_b200_ctx *c, Device &d) {
     const tfhe_b200_params &p = c->prm;
     if (d.ksk_tc) { CU(c, cudaFree(d.ksk_tc)); d.ksk_tc = nullptr; }
     if (!keyswitch_tc_supported(p.basebit, p.iks_t, kN, c->ksk_pitch)) return 0;
-    CU(c, cudaMalloc(&d.ksk_tc, keyswitch_tc_key_bytes(c->ksk_pitch, p.iks_t)));
-    CU(c, launch_ksk_to_tc(d.ksk, d.ksk_tc, p.iks_t, c->ksk_pitch, d.stream, &c->launches));
+    CU(c, cudaMalloc(&d.ksk_tc, keyswitch_tc_key_bytes(c->ksk_pitch, p.basebit, p.iks_t)));
+    CU(c, launch_ksk_to_tc(d.ksk, d.ksk_tc, p.basebit, p.iks_t, c->ksk_pitch, d.stream, &c->launches));
     CU(c, cudaStreamSynchronize(d.stream));
     return 0;
 }
@@ -1090,7 +1090,7 @@ static int circuit_run_device(tfhe_b200_ctx *c, tfhe_b200_circuit *q, int k, con
             const void *old_w = pd.wires.p, *old_l = pd.lv1.p, *old_d = pd.ksdig.p;
             if (int r = ensure(c, pd.wires, q->n_slots * inst * w0 * 4)) return r;
             if (int r = ensure(c, pd.lv1, std::max<size_t>(q->max_width, 1) * inst * w1 * 4)) return r;
-            if (int r = ensure(c, pd.ksdig, std::max<size_t>(q->max_width, 1) * inst * keyswitch_tc_digit_words(c->prm.iks_t) * 8)) return r;
+            if (int r = ensure(c, pd.ksdig, std::max<size_t>(q->max_width, 1) * inst * keyswitch_tc_digit_words(c->prm.basebit, c->prm.iks_t) * 8)) return r;
             if ((old_w != pd.wires.p || old_l != pd.lv1.p || old_d != pd.ksdig.p) && pd.graph) { cudaGraphExecDestroy(pd.graph); pd.graph = nullptr; }
             uint32_t *wires = (uint32_t *)pd.wires.p;
             for (size_t i = 0; i < q->n_inputs; i++)

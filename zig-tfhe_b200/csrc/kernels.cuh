@@ -82,12 +82,12 @@ struct KsArgs {
 cudaError_t launch_keyswitch(const KsArgs &a, int sm_count, cudaStream_t s, uint64_t *launches);
 
 // K2t (keyswitch_tc.cu): the same key switch as an unsigned 8-bit tensor-core contraction (tcgen05.mma kind::i8) over the
-// one-hot expansion of the digits; BASEBIT = 2 sets, in_dim = N.  ksk_tc: launch_ksk_to_tc() image of the packed key
+// one-hot expansion of the digits; BASEBIT = 2, 4, 5 sets, in_dim = N.  ksk_tc: launch_ksk_to_tc() image of the packed key
 // (keyswitch_tc_key_bytes()); digits: scratch of B * keyswitch_tc_digit_words() u64.
 bool keyswitch_tc_supported(int basebit, int iks_t, int in_dim, int pitch);
-size_t keyswitch_tc_key_bytes(int pitch, int iks_t);
-size_t keyswitch_tc_digit_words(int iks_t);
-cudaError_t launch_ksk_to_tc(const uint32_t *ksk_packed, uint8_t *out, int iks_t, int pitch, cudaStream_t s, uint64_t *launches);
+size_t keyswitch_tc_key_bytes(int pitch, int basebit, int iks_t);
+size_t keyswitch_tc_digit_words(int basebit, int iks_t);      // 64-bit digit words (= K blocks) per ciphertext; 0 if unsupported
+cudaError_t launch_ksk_to_tc(const uint32_t *ksk_packed, uint8_t *out, int basebit, int iks_t, int pitch, cudaStream_t s, uint64_t *launches);
 cudaError_t launch_keyswitch_tc(const KsArgs &a, const uint8_t *ksk_tc, uint64_t *digits, cudaStream_t s, uint64_t *launches);
 
 // one-time key re-layout kernels

@@ -1,6 +1,6 @@
 // keyswitch_tc.cu -- K2t: identity key switching as an exact integer contraction on the 5th-generation tensor cores.
 //
-// Replaces trgsw.identityKeySwitching (src/trgsw.zig:471-502) for large batches on the BASEBIT = 2 sets:
+// Replaces trgsw.identityKeySwitching (src/trgsw.zig:471-502) for large batches on the BASEBIT = 2, 4 and 5 sets:
 //   res = (0, ..., 0, src.b) - sum_{i < N, j < t} KSK[i][j][k_ij],   k_ij = digit_j(src.a[i] + prec_offset), k_ij != 0
 // With the digits expanded to one-hot bytes the sum is a dense product
 //   S[ct][col] = sum_K onehot[ct][K] * KSK[K][col]   (K = 3 (i t + j) + k - 1, 27,648 values at the 128-bit set)
@@ -21,6 +21,10 @@
 // memory, so a plain cp.async.bulk suffices) into a 3-deep ring.  Warp 5: one thread issues the MMAs and commits
 // each stage back to the producers (tcgen05.commit -> mbarrier).
 //
+// Other bases: BASEBIT = 2 packs a pair into 3 one-hot bytes (k = 1, 2, 3; 32 pairs per 96-byte block).  BASEBIT = 4 / 5 (UINT2 /
+// UINT4, t = 3) use 2^BASEBIT bytes per pair, byte k hot for digit k, with an all-zero key row behind byte 0: 6 resp. 3 pairs
+// per block, so the block geometry (96 bytes, three K = 32 MMA steps) and everything downstream of the expansion are unchanged.
+//
 // Operand layout (both operands K-major, SWIZZLE_NONE): 8 rows x 16 bytes core matrices, 128 contiguous bytes each;
 // the six core matrices of a row group along K are contiguous (LBO = 128), row groups follow every 768 bytes (SBO).
 #include <cuda_runtime.h>
@@ -33,8 +37,9 @@ namespace tfhe_b200 {
 namespace {
 
 constexpr int kTcRows = 128;                       // ciphertexts per CTA (MMA M)
-constexpr int kTcPairsPerBlock = 32;               // (i, j) pairs per K block = one 64-bit digit word per ciphertext
-constexpr int kTcBlockK = 3 * kTcPairsPerBlock;    // 96 one-hot bytes
+constexpr int kTcBlockK = 96;                      // one-hot bytes per K block = three K = 32 MMA steps = one 64-bit digit word per ciphertext
+__host__ __device__ constexpr int tc_pair_bytes(int basebit) { return basebit == 2 ? 3 : (1 << basebit); }
+__host__ __device__ constexpr int tc_pairs_per_block(int basebit) { return kTcBlockK / tc_pair_bytes(basebit); }   // 32, 6 (BASEBIT 4), 3 (BASEBIT 5)
 constexpr int kTcCores = kTcBlockK / 16;           // 6 core matrices along K
 constexpr int kTcLbo = 128, kTcSbo = kTcCores * 128;
 constexpr int kTcGroupCols = 128;                  // output columns per CTA (x 4 planes = 512 accumulator columns)
@@ -74,47 +79,52 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                  : "memory");
 }
 
-// digit stream: word w of ciphertext ct holds the 2-bit digits of pairs 32 w .. 32 w + 31 (pair p = i t + j at bits 2 (p & 31))
-__global__ void ks_digits_kernel(const uint32_t *__restrict__ lv1, uint64_t *__restrict__ ds, uint32_t B, int t, int words) {
+// digit stream: word w of ciphertext ct holds the BASEBIT-bit digits of the pairs of K block w (pair p = i t + j), pair q of the block at
+// bits BASEBIT * q
+__global__ void ks_digits_kernel(const uint32_t *__restrict__ lv1, uint64_t *__restrict__ ds, uint32_t B, int t, int words, int basebit) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (size_t)B * words) return;
     const size_t ct = idx / words;
     const int w = (int)(idx - ct * words);
-    const uint32_t prec_offset = 1u << (32 - (1 + 2 * t));          // trgsw.zig:483
+    const int ppb = tc_pairs_per_block(basebit);
+    const uint32_t prec_offset = 1u << (32 - (1 + basebit * t));    // trgsw.zig:483
+    const uint32_t kmask = (1u << basebit) - 1u;
     const uint32_t *a = lv1 + ct * (size_t)(kN + 1);
     uint64_t word = 0;
-    int p = w * kTcPairsPerBlock;
+    int p = w * ppb;
     int i = p / t, j = p - i * t;
     uint32_t abar = a[i] + prec_offset;
-    for (int q = 0; q < kTcPairsPerBlock; q++) {
-        const uint64_t k = (abar >> (32 - 2 * (j + 1))) & 3u;       // trgsw.zig:488-489
-        word |= k << (2 * q);
+    for (int q = 0; q < ppb; q++) {
+        const uint64_t k = (abar >> (32 - basebit * (j + 1))) & kmask;   // trgsw.zig:488-489
+        word |= k << (basebit * q);
         if (++j == t) {
             j = 0;
             i++;
-            if (q + 1 < kTcPairsPerBlock) abar = a[i] + prec_offset;
+            if (q + 1 < ppb) abar = a[i] + prec_offset;
         }
     }
     ds[idx] = word;
 }
 
-// one-time re-layout: packed key [pairs][3][pitch] u32 -> tensor-core key [group][block][operand tile], byte planes split.
-// Tile row = plane * W + column-in-group, tile K byte = 3 * (pair in block) + (k - 1).
-__global__ void ksk_to_tc_kernel(const uint32_t *__restrict__ ksk, uint8_t *__restrict__ out, int pitch, int nblocks) {
+// one-time re-layout: packed key [pairs][base - 1][pitch] u32 -> tensor-core key [group][block][operand tile], byte planes split.
+// Tile row = plane * W + column-in-group; tile K byte = (pair in block) * pair_bytes + slot, slot = k - 1 (BASEBIT 2) or k (else: slot 0 = zeros).
+__global__ void ksk_to_tc_kernel(const uint32_t *__restrict__ ksk, uint8_t *__restrict__ out, int pitch, int nblocks, int basebit) {
     const int g = blockIdx.y, b = blockIdx.x;
     const int W = tc_group_width(pitch, g);
+    const int pb = tc_pair_bytes(basebit), ppb = tc_pairs_per_block(basebit), rows_per_pair = (1 << basebit) - 1;
     uint8_t *tile = out + tc_group_offset(pitch, g, nblocks) + (size_t)b * (4 * W * kTcBlockK);
     const int total = 4 * W * kTcBlockK;
     for (int e = threadIdx.x; e < total; e += blockDim.x) {
-        // e enumerates (row, kb) in source-friendly order: kb fastest within a row would scatter the reads; take column fastest
-        const int kb = e / (4 * W), r = e - kb * (4 * W);
+        const int kb = e / (4 * W), r = e - kb * (4 * W);      // key column fastest: coalesced reads of a key row
         const int plane = r / W, cc = r - plane * W;
-        const int pair = b * kTcPairsPerBlock + kb / 3, k = kb % 3;
-        const uint32_t v = ksk[((size_t)pair * 3 + k) * pitch + g * kTcGroupCols + cc];
+        const int pair = b * ppb + kb / pb, slot = kb % pb;
+        const int krow = basebit == 2 ? slot : slot - 1;       // row of the packed key (digit k = krow + 1), -1: the zero row of digit 0
+        const uint32_t v = krow < 0 ? 0u : ksk[((size_t)pair * rows_per_pair + krow) * pitch + g * kTcGroupCols + cc];
         tile[tc_tile_offset(r, kb)] = (uint8_t)(v >> (8 * plane));
     }
 }
 
+template <int BASEBIT>
 __global__ void __launch_bounds__(kTcThreads, 1)
     keyswitch_tc_kernel(const uint64_t *__restrict__ ds, const uint8_t *__restrict__ ksk_tc, const uint32_t *__restrict__ lv1, uint32_t *__restrict__ lv0,
                         uint32_t B, int n, int pitch, int nblocks) {
@@ -164,17 +174,28 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             const uint64_t dw = next;
             if (live && kb + 1 < nblocks) next = __ldg(my_ds + kb + 1);
             uint32_t w[24];
+            if (BASEBIT == 2) {
 #pragma unroll
-            for (int q4 = 0; q4 < 8; q4++) {       // four pairs -> three words
-                uint32_t v[4];
+                for (int q4 = 0; q4 < 8; q4++) {       // four pairs -> three words
+                    uint32_t v[4];
 #pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    const uint32_t k8 = (uint32_t)((dw >> (2 * (4 * q4 + e))) & 3ull) << 3;
-                    v[e] = (1u << k8) >> 8;         // k = 0: no byte; k = 1, 2, 3: byte k - 1 of the pair's three
+                    for (int e = 0; e < 4; e++) {
+                        const uint32_t k8 = (uint32_t)((dw >> (2 * (4 * q4 + e))) & 3ull) << 3;
+                        v[e] = (1u << k8) >> 8;         // k = 0: no byte; k = 1, 2, 3: byte k - 1 of the pair's three
+                    }
+                    w[3 * q4] = v[0] | (v[1] << 24);
+                    w[3 * q4 + 1] = (v[1] >> 8) | (v[2] << 16);
+                    w[3 * q4 + 2] = (v[2] >> 16) | (v[3] << 8);
                 }
-                w[3 * q4] = v[0] | (v[1] << 24);
-                w[3 * q4 + 1] = (v[1] >> 8) | (v[2] << 16);
-                w[3 * q4 + 2] = (v[2] >> 16) | (v[3] << 8);
+            } else {                                   // 2^BASEBIT bytes per pair, byte k hot (byte 0 meets the zero row)
+                constexpr int kWordsPerPair = (1 << BASEBIT) / 4, kPairs = 24 / kWordsPerPair;
+#pragma unroll
+                for (int p = 0; p < kPairs; p++) {
+                    const uint32_t k = (uint32_t)(dw >> (BASEBIT * p)) & ((1u << BASEBIT) - 1u);
+                    const uint32_t hot = 1u << (8u * (k & 3u));
+#pragma unroll
+                    for (int q = 0; q < kWordsPerPair; q++) w[p * kWordsPerPair + q] = ((k >> 2) == (uint32_t)q) ? hot : 0u;
+                }
             }
             mbar_wait(&empty_bar[s], ph ^ 1u);
             unsigned char *dst = row_base + s * kTcABytes;
@@ -258,33 +279,35 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
 }  // namespace
 
-size_t keyswitch_tc_key_bytes(int pitch, int iks_t) { return (size_t)kN * iks_t * 3 * pitch * 4; }
-size_t keyswitch_tc_digit_words(int iks_t) { return (size_t)kN * iks_t / kTcPairsPerBlock; }
 bool keyswitch_tc_supported(int basebit, int iks_t, int in_dim, int pitch) {
-    return basebit == 2 && in_dim == kN && (kN * iks_t) % kTcPairsPerBlock == 0 && pitch % 4 == 0 && pitch >= 16;
+    if (basebit != 2 && basebit != 4 && basebit != 5) return false;      // pair_bytes must divide the 96-byte block
+    return in_dim == kN && (kN * iks_t) % tc_pairs_per_block(basebit) == 0 && basebit * tc_pairs_per_block(basebit) <= 64 && pitch % 4 == 0 && pitch >= 16;
 }
+size_t keyswitch_tc_digit_words(int basebit, int iks_t) { return keyswitch_tc_supported(basebit, iks_t, kN, 16) ? (size_t)kN * iks_t / tc_pairs_per_block(basebit) : 0; }
+size_t keyswitch_tc_key_bytes(int pitch, int basebit, int iks_t) { return keyswitch_tc_digit_words(basebit, iks_t) * kTcBlockK * (size_t)pitch * 4; }
 
-cudaError_t launch_ksk_to_tc(const uint32_t *ksk_packed, uint8_t *out, int iks_t, int pitch, cudaStream_t s, uint64_t *launches) {
-    const int nblocks = kN * iks_t / kTcPairsPerBlock;
+cudaError_t launch_ksk_to_tc(const uint32_t *ksk_packed, uint8_t *out, int basebit, int iks_t, int pitch, cudaStream_t s, uint64_t *launches) {
+    const int nblocks = (int)keyswitch_tc_digit_words(basebit, iks_t);
     const int groups = (pitch + kTcGroupCols - 1) / kTcGroupCols;
-    ksk_to_tc_kernel<<<dim3(nblocks, groups), 256, 0, s>>>(ksk_packed, out, pitch, nblocks);
+    ksk_to_tc_kernel<<<dim3(nblocks, groups), 256, 0, s>>>(ksk_packed, out, pitch, nblocks, basebit);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }
 
 cudaError_t launch_keyswitch_tc(const KsArgs &a, const uint8_t *ksk_tc, uint64_t *digits, cudaStream_t s, uint64_t *launches) {
     if (a.B == 0) return cudaSuccess;
-    const int nblocks = kN * a.iks_t / kTcPairsPerBlock;
+    const int nblocks = (int)keyswitch_tc_digit_words(a.basebit, a.iks_t);
     const int groups = (a.pitch + kTcGroupCols - 1) / kTcGroupCols;
     const size_t words = (size_t)a.B * nblocks;
-    ks_digits_kernel<<<(unsigned)((words + 255) / 256), 256, 0, s>>>(a.lv1, digits, a.B, a.iks_t, nblocks);
+    ks_digits_kernel<<<(unsigned)((words + 255) / 256), 256, 0, s>>>(a.lv1, digits, a.B, a.iks_t, nblocks, a.basebit);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const size_t smem = (size_t)kTcStages * (kTcABytes + kTcBBytesMax) + (2 * kTcStages + 1) * 8 + 16;
-    e = cudaFuncSetAttribute(keyswitch_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = a.basebit == 2 ? keyswitch_tc_kernel<2> : a.basebit == 4 ? keyswitch_tc_kernel<4> : keyswitch_tc_kernel<5>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const dim3 grid(groups, (a.B + kTcRows - 1) / kTcRows);
-    keyswitch_tc_kernel<<<grid, kTcThreads, smem, s>>>(digits, ksk_tc, a.lv1, a.lv0, a.B, a.n, a.pitch, nblocks);
+    kern<<<grid, kTcThreads, smem, s>>>(digits, ksk_tc, a.lv1, a.lv0, a.B, a.n, a.pitch, nblocks);
     if (launches) (*launches) += 2;
     return cudaGetLastError();
 }
