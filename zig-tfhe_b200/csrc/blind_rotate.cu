@@ -62,7 +62,11 @@ constexpr bool kRingLastArriver = false;
 #else
 constexpr bool kRingLastArriver = true;
 #endif
-constexpr bool kUnrollL3 = true;   // L = 3 / BGBIT = 6 instantiation of the throughput kernel (false: generic kernel only, for A/B runs)
+#ifdef TFHE_B200_NO_LT3
+constexpr bool kUnrollL3 = false;
+#else
+constexpr bool kUnrollL3 = true;
+#endif   // L = 3 / BGBIT = 6 instantiation of the throughput kernel (false: generic kernel only, for A/B runs)
 
 // Twiddles r^1..r^7 of one thread for one pass.  MODE 0: all seven resident (28 registers, KCT <= 4);
 // MODE 1: r, r^2, r^4 resident and the rest expanded per pass (12 registers); MODE 2: read from a shared-memory
@@ -939,7 +943,7 @@ cudaError_t launch_twt(const BrArgs &a, cudaStream_t s) {
     using Lay = Layout<KCT, TEAM, (KCT > 4)>;
     const size_t smem = Lay::kStages * kBskChunkBytes + 96 + (size_t)KCT * Lay::group_bytes(a.n);
     auto kern = blind_rotate_kernel<KCT, true, false, TEAM, 0, 1>;
-    if (a.L == 3 && a.bgbit == 6 && !a.wide_round) kern = blind_rotate_kernel<KCT, true, false, TEAM, 3, 1>;
+    if (a.L == 3 && a.bgbit == 6 && !a.wide_round && kUnrollL3) kern = blind_rotate_kernel<KCT, true, false, TEAM, 3, 1>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<(a.B + KCT - 1) / KCT, KCT * kGroupThreads, smem, s>>>(a);

@@ -259,7 +259,10 @@ constexpr int kExStages = 3;
 __host__ __device__ constexpr int ex_group_bytes(int n, bool dense) { return 2 * kN * 4 + (dense ? 0 : kX1Slots * 16) + 2 * kX2Slots * 16 + align16((n + 1) * 2); }
 __host__ __device__ constexpr int ex_fixed_bytes() { return kExStages * kBskChunkBytes + 112 + kExactSharedTabCplx * 16; }
 
-template <int KCT, bool MARGIN>
+// LT / BGT > 0: gadget length and digit width as compile-time constants (digit loop unrolled, shifts and masks folded), as in the
+// fast kernel, where that instantiation is worth 6 % (profiles/r02_k1_ring.log); instantiated for L = 1 / BGBIT = 22 (UINT4 ... UINT8):
+// 126.7 k -> 136.9 k UINT4 bootstraps/s (profiles/r02_k1x_dense.log).
+template <int KCT, bool MARGIN, int LT = 0, int BGT = 0>
 __global__ void __launch_bounds__(KCT * kGroupThreads, 1)
     blind_rotate_exact_rb_kernel(const BrArgs P, const double *__restrict__ tables, const cplx *__restrict__ bsk_x,
                                  const cplx *__restrict__ shared_tab, const ExactConsts kc) {
@@ -275,7 +278,7 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1)
     ptr += 112;
     cplx *twist = reinterpret_cast<cplx *>(ptr);     // [512] in acc_pos order
     ptr += kExactSharedTabCplx * 16;
-    const int n = P.n, L = P.L, bgbit = P.bgbit;
+    const int n = P.n, L = LT > 0 ? LT : P.L, bgbit = BGT > 0 ? BGT : P.bgbit;
     const int tid = threadIdx.x;
     const int first_ct = blockIdx.x * KCT;
     const int n_active = min(KCT, (int)P.B - first_ct);
@@ -386,7 +389,7 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1)
             const uint32_t *accp = h ? acc_b : acc_a;
             uint32_t d[16];
             load_rot_diffs(d, accp, at, offset, hi, lo);
-#pragma unroll 1
+#pragma unroll (LT > 0 ? LT : 1)
             for (int l = 0; l < L; l++) {
                 const int sh = 32 - (l + 1) * bgbit;
                 cplx v[8];
@@ -464,6 +467,8 @@ cudaError_t launch_rb(const BrArgs &a, const ExactArgs &x, const ExactConsts &kc
     const size_t smem = ex_fixed_bytes() + (size_t)KCT * ex_group_bytes(a.n, KCT > 4);
     auto k0 = blind_rotate_exact_rb_kernel<KCT, false>;
     auto k1 = blind_rotate_exact_rb_kernel<KCT, true>;
+    if (KCT >= 4 && a.L == 1 && a.bgbit == 22) k0 = blind_rotate_exact_rb_kernel<KCT, false, (KCT >= 4 ? 1 : 0), (KCT >= 4 ? 22 : 0)>;   // UINT4 (and UINT5-8)
+    // (L = 3 / BGBIT = 6 the same way: 76.1 k against 77.0 k bootstraps/s at the 128-bit set in exact mode -- the unrolled digit loop spills; not instantiated)
     cudaError_t e = cudaFuncSetAttribute(margin ? k1 : k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const unsigned grid = (a.B + KCT - 1) / KCT;
