@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
     bar_sync(barid, kTeamThreads);
 
     const uint32_t mask = (1u << bgbit) - 1u, half_bg = 1u << (bgbit - 1);
-    const uint32_t offset = P.offset;
+    const uint32_t offset = LT == 3 ? 0x82080000u : P.offset;   // genDecompositionOffset for L = 3 / BGBIT = 6 (src/key.zig:121-131); the launcher checks it
     const int wide = LT == 3 ? 0 : P.wide_round;   // BGBIT = 6: magic-add rounding (coefficients < 2^45)
     int stage = 0;
     uint32_t phase = 0;
@@ -943,7 +943,7 @@ cudaError_t launch_twt(const BrArgs &a, cudaStream_t s) {
     using Lay = Layout<KCT, TEAM, (KCT > 4)>;
     const size_t smem = Lay::kStages * kBskChunkBytes + 96 + (size_t)KCT * Lay::group_bytes(a.n);
     auto kern = blind_rotate_kernel<KCT, true, false, TEAM, 0, 1>;
-    if (a.L == 3 && a.bgbit == 6 && !a.wide_round && kUnrollL3) kern = blind_rotate_kernel<KCT, true, false, TEAM, 3, 1>;
+    if (a.L == 3 && a.bgbit == 6 && a.offset == 0x82080000u && !a.wide_round && kUnrollL3) kern = blind_rotate_kernel<KCT, true, false, TEAM, 3, 1>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<(a.B + KCT - 1) / KCT, KCT * kGroupThreads, smem, s>>>(a);
@@ -958,7 +958,7 @@ cudaError_t launch_variant(const BrArgs &a, cudaStream_t s) {
     auto kern = blind_rotate_kernel<KCT, USE_TMA, MARGIN, TEAM>;
     // the L = 3 / BGBIT = 6 sets (80/110/128-bit) get their own instantiation: digit loop unrolled, shifts, masks and the
     // rounding mode compile-time (+5 % on the 128-bit bench; profiles/r01_wave_scaling.log)
-    if (KCT <= 4 && USE_TMA && !MARGIN && a.L == 3 && a.bgbit == 6 && !a.wide_round && kUnrollL3)
+    if (KCT <= 4 && USE_TMA && !MARGIN && a.L == 3 && a.bgbit == 6 && a.offset == 0x82080000u && !a.wide_round && kUnrollL3)
         kern = blind_rotate_kernel<KCT, USE_TMA, MARGIN, TEAM, (KCT <= 4 && USE_TMA && !MARGIN) ? 3 : 0>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
