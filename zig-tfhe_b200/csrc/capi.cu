@@ -44,6 +44,10 @@ struct Device {
     Buf a, b, out, lv1, ops, tv, trlwe, lut, ksdig;
     void *stage[2] = {nullptr, nullptr};            // host_copy: pinned staging buffers (allocated on first use)
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    // pipelined host batches (run_host_device_pipelined): second set of batch buffers, a copy stream, hand-over events
+    cudaStream_t copy_stream = nullptr;
+    Buf a2, b2, out2, ops2;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // K1 start, K1 end / K2 start, K2 end (timing mode)
     bool ev_valid = false;
     uint64_t launches = 0;             // kernels launched on this device by its host thread (summed by tfhe_b200_launch_count)
@@ -68,6 +72,7 @@ struct tfhe_b200_ctx {
     bool timing = false;
     int ks_tile = 0, ks_vec = 0, ks_fill = 0, ks_rot = 0;   // key-switch tuning overrides (0 = automatic)
     int inject_fault = 0;                 // test hook (tuning key "inject_fault"): device k = value - 1 fails its next host-batch shard
+    int host_pipeline = 1;                // large host batches from pageable memory: overlap the staging of chunk k + 1 with the kernels of chunk k
     int host_copy_threads = 8;            // large copies from / to PAGEABLE caller memory are staged through pinned buffers by this many
                                           // memcpy threads (0 = plain cudaMemcpyAsync from the caller's buffer)
     int ks_tc = 0;                        // tensor-core key switch: 0 = automatic (batches >= ks_tc_min), 1 = always, -1 = never
@@ -227,16 +232,19 @@ void parallel_memcpy(void *dst, const void *src, size_t bytes, int T) {
     for (auto &w : workers) w.join();
 }
 
-int host_copy(tfhe_b200_ctx *c, Device &d, void *dst, const void *src, size_t bytes, cudaMemcpyKind kind) {
+bool is_pageable(const void *host) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
+int host_copy(tfhe_b200_ctx *c, Device &d, void *dst, const void *src, size_t bytes, cudaMemcpyKind kind, cudaStream_t stream = nullptr) {
+    if (!stream) stream = d.stream;
     const void *host = kind == cudaMemcpyHostToDevice ? src : dst;
     bool staged = c->host_copy_threads > 0 && bytes >= kStagePiece;
-    if (staged) {
-        cudaPointerAttributes at{};
-        if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); staged = false; }
-        else staged = at.type == cudaMemoryTypeUnregistered;
-    }
+    if (staged) staged = is_pageable(host);
     if (!staged) {
-        CU(c, cudaMemcpyAsync(dst, src, bytes, kind, d.stream));
+        CU(c, cudaMemcpyAsync(dst, src, bytes, kind, stream));
         return 0;
     }
     for (int k = 0; k < 2; k++) {
@@ -251,8 +259,8 @@ int host_copy(tfhe_b200_ctx *c, Device &d, void *dst, const void *src, size_t by
             const int k = (int)(p & 1);
             if (p >= 2) CU(c, cudaEventSynchronize(d.stage_ev[k]));          // the DMA that last read this staging buffer
             parallel_memcpy(d.stage[k], (const char *)src + off, nb, T);
-            CU(c, cudaMemcpyAsync((char *)dst + off, d.stage[k], nb, cudaMemcpyHostToDevice, d.stream));
-            CU(c, cudaEventRecord(d.stage_ev[k], d.stream));
+            CU(c, cudaMemcpyAsync((char *)dst + off, d.stage[k], nb, cudaMemcpyHostToDevice, stream));
+            CU(c, cudaEventRecord(d.stage_ev[k], stream));
         }
         CU(c, cudaEventSynchronize(d.stage_ev[(pieces - 1) & 1]));              // staging buffers are free again for the next call
         if (pieces > 1) CU(c, cudaEventSynchronize(d.stage_ev[(pieces - 2) & 1]));
@@ -260,8 +268,8 @@ int host_copy(tfhe_b200_ctx *c, Device &d, void *dst, const void *src, size_t by
         for (size_t p = 0; p < pieces + 1; p++) {                               // DMA of piece p overlaps the memcpy of piece p - 1
             if (p < pieces) {
                 const size_t off = p * kStagePiece, nb = std::min(kStagePiece, bytes - off);
-                CU(c, cudaMemcpyAsync(d.stage[p & 1], (const char *)src + off, nb, cudaMemcpyDeviceToHost, d.stream));
-                CU(c, cudaEventRecord(d.stage_ev[p & 1], d.stream));
+                CU(c, cudaMemcpyAsync(d.stage[p & 1], (const char *)src + off, nb, cudaMemcpyDeviceToHost, stream));
+                CU(c, cudaEventRecord(d.stage_ev[p & 1], stream));
             }
             if (p >= 1) {
                 const size_t q = p - 1, off = q * kStagePiece, nb = std::min(kStagePiece, bytes - off);
@@ -277,6 +285,69 @@ int host_copy(tfhe_b200_ctx *c, Device &d, void *dst, const void *src, size_t by
 // launch, copy back), the stand-in for the reference's CPU thread pool (src/parallel/thread_pool.zig:39-83).  Copies
 // from pageable host memory block the issuing thread, so one thread per device is what lets the H2D / D2H traffic of
 // all devices (each on its own PCIe link) and their kernels proceed concurrently.
+// Gate / bootstrap batches of one device from PAGEABLE host memory, pipelined: the shard is cut into four chunks of whole CTA
+// waves; while the kernels of chunk k run on the device's stream, this thread stages the inputs of chunk k + 1 through pinned
+// memory on a copy stream and then the outputs of chunk k - 1.  Two sets of batch buffers; events hand a chunk from the copy
+// stream to the compute stream and back.  (From pinned memory the copies are 1.5 % of a step and every extra kernel boundary
+// costs a ragged K1 tail, so pinned callers keep the single launch pair: DESIGN.md section 6.)
+int run_host_device_pipelined(tfhe_b200_ctx *c, Device &d, size_t lo, size_t hi, int op, const int32_t *ops, const uint32_t *a, const uint32_t *b,
+                              uint32_t *out, const uint32_t *tv) {
+    const size_t w0 = (size_t)c->prm.n + 1;
+    const bool two_inputs = (op >= 0 || ops);
+    CU(c, cudaSetDevice(d.id));
+    if (!d.copy_stream) CU(c, cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+        if (!d.ev_in[k]) CU(c, cudaEventCreateWithFlags(&d.ev_in[k], cudaEventDisableTiming));
+        if (!d.ev_done[k]) CU(c, cudaEventCreateWithFlags(&d.ev_done[k], cudaEventDisableTiming));
+    }
+    const uint32_t *d_tv = nullptr;
+    if (tv) {
+        if (int r = ensure(c, d.tv, (size_t)2 * kN * 4)) return r;
+        CU(c, cudaMemcpyAsync(d.tv.p, tv, (size_t)2 * kN * 4, cudaMemcpyHostToDevice, d.stream));
+        d_tv = (const uint32_t *)d.tv.p;
+    }
+    const size_t wave = (size_t)6 * (d.sm_count > 0 ? d.sm_count : 148);
+    size_t chunk = (((hi - lo + 3) / 4 + wave - 1) / wave) * wave;
+    chunk = std::min(chunk, c->max_chunk);
+    Buf *A[2] = {&d.a, &d.a2}, *Bb[2] = {&d.b, &d.b2}, *O[2] = {&d.out, &d.out2}, *Ops[2] = {&d.ops, &d.ops2};
+    size_t prev_off = 0, prev_nb = 0;
+    int k = 0;
+    for (size_t off = lo; off < hi; off += chunk, k++) {
+        const size_t nb = std::min(chunk, hi - off);
+        const int p = k & 1;
+        if (int r = ensure(c, *A[p], nb * w0 * 4)) return r;
+        if (int r = ensure(c, *O[p], nb * w0 * 4)) return r;
+        if (int r = host_copy(c, d, A[p]->p, a + off * w0, nb * w0 * 4, cudaMemcpyHostToDevice, d.copy_stream)) return r;
+        if (two_inputs) {
+            if (int r = ensure(c, *Bb[p], nb * w0 * 4)) return r;
+            if (int r = host_copy(c, d, Bb[p]->p, b + off * w0, nb * w0 * 4, cudaMemcpyHostToDevice, d.copy_stream)) return r;
+        }
+        const int32_t *d_ops = nullptr;
+        if (ops) {
+            if (int r = ensure(c, *Ops[p], nb * 4)) return r;
+            CU(c, cudaMemcpyAsync(Ops[p]->p, ops + off, nb * 4, cudaMemcpyHostToDevice, d.copy_stream));
+            d_ops = (const int32_t *)Ops[p]->p;
+        }
+        CU(c, cudaEventRecord(d.ev_in[p], d.copy_stream));
+        CU(c, cudaStreamWaitEvent(d.stream, d.ev_in[p], 0));
+        if (int r = run_device(c, d, ops ? 0 : op, d_ops, (uint32_t *)A[p]->p, two_inputs ? (uint32_t *)Bb[p]->p : nullptr, (uint32_t *)O[p]->p, nullptr, nullptr,
+                               nb, d_tv, 0))
+            return r;
+        CU(c, cudaEventRecord(d.ev_done[p], d.stream));
+        if (k >= 1) {   // results of the previous chunk; its buffers are written again only by chunk k + 1, enqueued behind this copy
+            CU(c, cudaStreamWaitEvent(d.copy_stream, d.ev_done[p ^ 1], 0));
+            if (int r = host_copy(c, d, out + prev_off * w0, O[p ^ 1]->p, prev_nb * w0 * 4, cudaMemcpyDeviceToHost, d.copy_stream)) return r;
+        }
+        prev_off = off;
+        prev_nb = nb;
+    }
+    CU(c, cudaStreamWaitEvent(d.copy_stream, d.ev_done[(k - 1) & 1], 0));
+    if (int r = host_copy(c, d, out + prev_off * w0, O[(k - 1) & 1]->p, prev_nb * w0 * 4, cudaMemcpyDeviceToHost, d.copy_stream)) return r;
+    CU(c, cudaStreamSynchronize(d.copy_stream));
+    CU(c, cudaStreamSynchronize(d.stream));
+    return 0;
+}
+
 int run_host_device(tfhe_b200_ctx *c, Device &d, size_t lo, size_t hi, int op, const int32_t *ops, const uint32_t *a, const uint32_t *b,
                     void *out, Out kind, const uint32_t *tv, int tv_per_item, int lut_m) {
     const size_t w0 = (size_t)c->prm.n + 1, w1 = (size_t)kN + 1, wt = (size_t)2 * kN;
@@ -286,6 +357,8 @@ int run_host_device(tfhe_b200_ctx *c, Device &d, size_t lo, size_t hi, int op, c
         c->inject_fault = 0;       // one shot: the context must be usable again afterwards
         return fail(c, TFHE_B200_ERR_CUDA, "injected fault on device %d (test hook)", d.id);
     }
+    if (c->host_pipeline != 0 && kind == Out::LV0 && !(tv && (tv_per_item || lut_m > 0)) && hi - lo >= 32768 && !c->timing && is_pageable(a + lo * w0))
+        return run_host_device_pipelined(c, d, lo, hi, op, ops, a, b, (uint32_t *)out, tv);
     for (size_t off = lo; off < hi; off += c->max_chunk) {
         const size_t nb = std::min(c->max_chunk, hi - off);
         CU(c, cudaSetDevice(d.id));
@@ -583,7 +656,12 @@ void tfhe_b200_destroy(tfhe_b200_ctx *c) {
         for (int k = 0; k < 2; k++) {
             if (d.stage[k]) cudaFreeHost(d.stage[k]);
             if (d.stage_ev[k]) cudaEventDestroy(d.stage_ev[k]);
+            if (d.ev_in[k]) cudaEventDestroy(d.ev_in[k]);
+            if (d.ev_done[k]) cudaEventDestroy(d.ev_done[k]);
         }
+        for (void *p : {d.a2.p, d.b2.p, d.out2.p, d.ops2.p})
+            if (p) cudaFree(p);
+        if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
         if (d.stream) cudaStreamDestroy(d.stream);
     }
     delete c;
@@ -1210,6 +1288,7 @@ int tfhe_b200_set_tuning(tfhe_b200_ctx *c, const char *key, int value) {
     else if (!strcmp(key, "ks_fill")) c->ks_fill = value;
     else if (!strcmp(key, "ks_rot")) c->ks_rot = value;
     else if (!strcmp(key, "inject_fault")) c->inject_fault = value;
+    else if (!strcmp(key, "host_pipeline")) c->host_pipeline = value;
     else if (!strcmp(key, "host_copy_threads")) c->host_copy_threads = std::max(0, std::min(value, 16));
     else if (!strcmp(key, "ks_tc")) c->ks_tc = value;
     else if (!strcmp(key, "ks_tc_min")) c->ks_tc_min = value;
