@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (DENSE && tid < 32) {
-        tmem_alloc(tmem_slot, 256);     // 64 columns per warp, three warps per lane quadrant
+        tmem_alloc(tmem_slot, 512);     // 96 columns per warp (stage twiddles + twist), three warps per lane quadrant
         tmem_fence_before_sync();
     }
     for (int j = tid; j < kExactSharedTabCplx; j += KCT * kGroupThreads) twist[j] = shared_tab[j];
@@ -319,7 +319,17 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1)
     // per-thread stage twiddles (forward table; the inverse direction uses their exact conjugates)
     ExTwSrc<DENSE> tw;
     if (DENSE) {
-        tw.taddr = tmem_base + ((uint32_t)((tid >> 5) & 3) << 21) + (uint32_t)(tid >> 7) * 64u;
+        tw.taddr = tmem_base + ((uint32_t)((tid >> 5) & 3) << 21) + (uint32_t)(tid >> 7) * 96u;
+        {   // this thread's eight twist values (coefficients 64 p + 8 lo + hi) in columns [64, 96) of its window
+            uint32_t r[32];
+#pragma unroll
+            for (int p = 0; p < 8; p++) {
+                const cplx w = twist[64 * p + t];
+                r[4 * p] = (uint32_t)__double2loint(w.re); r[4 * p + 1] = (uint32_t)__double2hiint(w.re);
+                r[4 * p + 2] = (uint32_t)__double2loint(w.im); r[4 * p + 3] = (uint32_t)__double2hiint(w.im);
+            }
+            tmem_st32(tw.taddr + 64u, r);
+        }
         ex_tw_park(tw.taddr, ex_twiddles_b(tables + 2 * kExactTabStride, tables + 3 * kExactTabStride, lo));
         ex_tw_park(tw.taddr + 32u, ex_twiddles_c(tables + 2 * kExactTabStride, tables + 3 * kExactTabStride, 8 * lo + hi));
         tmem_wait_st();
@@ -393,11 +403,18 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1)
             for (int l = 0; l < L; l++) {
                 const int sh = 32 - (l + 1) * bgbit;
                 cplx v[8];
+                uint32_t twr[32];
+                if (DENSE) {      // twist values from tensor memory (shared-memory table otherwise)
+                    tmem_ld32(tw.taddr + 64u, twr);
+                    tmem_wait_ld();
+                }
 #pragma unroll
                 for (int p = 0; p < 8; p++) {     // decomposition digit (trgsw.zig:208-217), fold + twist (fft.zig:297-334)
                     const double x_re = (double)(int32_t)(((d[2 * p] >> sh) & mask) - half_bg);
                     const double x_im = (double)(int32_t)(((d[2 * p + 1] >> sh) & mask) - half_bg);
-                    v[p] = ex_twist(x_re, x_im, twist[64 * p + t]);
+                    const cplx w = DENSE ? cplx{__hiloint2double((int)twr[4 * p + 1], (int)twr[4 * p]), __hiloint2double((int)twr[4 * p + 3], (int)twr[4 * p + 2])}
+                                         : twist[64 * p + t];
+                    v[p] = ex_twist(x_re, x_im, w);
                 }
                 ex_transform<false, DENSE>(v, xb, tw, kc, hi, lo, barid, pr);
                 if (DENSE) mbar_wait(&full_bar[stage], phase);
@@ -425,9 +442,16 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1)
                 for (int q = 0; q < 8; q++) oa[q] = ob[q];
             }
             ex_transform<true, DENSE>(oa, xb, tw, kc, hi, lo, barid, pr);
+            uint32_t twr[32];
+            if (DENSE) {
+                tmem_ld32(tw.taddr + 64u, twr);
+                tmem_wait_ld();
+            }
 #pragma unroll
             for (int p = 0; p < 8; p++) {
-                const cplx r = ex_untwist(oa[p], twist[64 * p + t]);
+                const cplx w = DENSE ? cplx{__hiloint2double((int)twr[4 * p + 1], (int)twr[4 * p]), __hiloint2double((int)twr[4 * p + 3], (int)twr[4 * p + 2])}
+                                     : twist[64 * p + t];
+                const cplx r = ex_untwist(oa[p], w);
                 double r_re, r_im;
                 const uint32_t u_re = ex_round_torus(r.re, &r_re), u_im = ex_round_torus(r.im, &r_im);
                 if (MARGIN) margin = fmax(margin, fmax(fabs(r.re - r_re), fabs(r.im - r_im)));
@@ -457,7 +481,7 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1)
         bar_sync(15, n_active * kGroupThreads);      // every active warp is done with its tensor-memory window
         if (tid < 32) {
             tmem_fence_after_sync();
-            tmem_dealloc(tmem_base, 256);
+            tmem_dealloc(tmem_base, 512);
         }
     }
 }
