@@ -149,3 +149,24 @@ def test_exact_register_blocked_equals_legacy_and_oracle(name, modulus):
         assert (c.bootstrap_batch(ct[:12], tvs, tv_per_item=True) == orc.bootstrap_batch(ct[:12], k, tvs, tv_per_item=True)).all()
     finally:
         c.close()
+
+
+def test_fast_mode_uint4_instantiations_agree():
+    """fast mode at UINT4 is not the parity mode, but its kernels must agree with each other: the L = 1 /
+    BGBIT = 22 instantiation of the six-per-CTA kernel (full waves) against the generic four-per-CTA kernel, word for word"""
+    import tfhe_b200
+    c, orc, k = _ctx("uint4", tfhe_b200.MODE_FAST)
+    try:
+        B = 148 * 6 + 40
+        rng = np.random.default_rng(12)
+        ct = orc.encrypt_lwe_messages(rng.integers(0, 16, B).astype(np.uint32), 16, k, seed=3)
+        tv = orc.lut_generate(np.arange(16, dtype=np.uint32), 16)
+        a = c.blind_rotate_batch(ct, tv)                 # 888 on the L = 1 instantiation + a 40-ciphertext tail
+        c.set_tuning("kct", 4)
+        b = c.blind_rotate_batch(ct, tv)
+        c.set_tuning("kct", 0); c.set_tuning("twt", -1)
+        d = c.blind_rotate_batch(ct, tv)                 # round-1 kernels
+        c.set_tuning("twt", 0)
+        assert (a == b).all() and (a == d).all()
+    finally:
+        c.close()

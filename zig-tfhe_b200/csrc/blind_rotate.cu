@@ -277,7 +277,8 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(ptr + 64);
     uint32_t *ring_cnt = reinterpret_cast<uint32_t *>(ptr + 80);   // [kMaxStages] releases per stage, monotone
     ptr += 96;
-    const int n = P.n, L = LT > 0 ? LT : P.L, bgbit = LT == 3 ? 6 : P.bgbit;   // LT = 3: the L = 3 / BGBIT = 6 sets (80/110/128-bit)
+    // LT = 3: the L = 3 / BGBIT = 6 sets (80/110/128-bit).  LT = 1: L = 1 / BGBIT = 22 (UINT4 ... UINT8; offset 2^31, wide rounding)
+    const int n = P.n, L = LT > 0 ? LT : P.L, bgbit = LT == 3 ? 6 : LT == 1 ? 22 : P.bgbit;
     static_assert(TEAM == 1 || (TEAM == 2 && KCT % 2 == 0), "a team never straddles CTAs");
     constexpr int kTeamThreads = TEAM * kGroupThreads;
     const int group_bytes = Lay::group_bytes(n);
@@ -410,8 +411,8 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
     bar_sync(barid, kTeamThreads);
 
     const uint32_t mask = (1u << bgbit) - 1u, half_bg = 1u << (bgbit - 1);
-    const uint32_t offset = LT == 3 ? 0x82080000u : P.offset;   // genDecompositionOffset for L = 3 / BGBIT = 6 (src/key.zig:121-131); the launcher checks it
-    const int wide = LT == 3 ? 0 : P.wide_round;   // BGBIT = 6: magic-add rounding (coefficients < 2^45)
+    const uint32_t offset = LT == 3 ? 0x82080000u : LT == 1 ? 0x80000000u : P.offset;   // genDecompositionOffset for L = 3 / BGBIT = 6 (src/key.zig:121-131); the launcher checks it
+    const int wide = LT == 3 ? 0 : LT == 1 ? 1 : P.wide_round;   // BGBIT = 6: magic-add rounding (coefficients < 2^45)
     int stage = 0;
     uint32_t phase = 0;
     double margin = 0.0;
@@ -944,6 +945,8 @@ cudaError_t launch_twt(const BrArgs &a, cudaStream_t s) {
     const size_t smem = Lay::kStages * kBskChunkBytes + 96 + (size_t)KCT * Lay::group_bytes(a.n);
     auto kern = blind_rotate_kernel<KCT, true, false, TEAM, 0, 1>;
     if (a.L == 3 && a.bgbit == 6 && a.offset == 0x82080000u && !a.wide_round && kUnrollL3) kern = blind_rotate_kernel<KCT, true, false, TEAM, 3, 1>;
+    if (KCT == 6 && a.L == 1 && a.bgbit == 22 && a.offset == 0x80000000u && a.wide_round && kUnrollL3)
+        kern = blind_rotate_kernel<KCT, true, false, TEAM, (KCT == 6 ? 1 : 0), 1>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<(a.B + KCT - 1) / KCT, KCT * kGroupThreads, smem, s>>>(a);
