@@ -8,7 +8,7 @@
 // tcgen05.mma kind::i8 with 32-bit integer accumulation in tensor memory.  At most N t = 9,216 rows are selected per
 // ciphertext, so a plane sum stays below 9,216 x 255 < 2^22: no overflow, and
 //   S = P0 + (P1 << 8) + (P2 << 16) + (P3 << 24)  (mod 2^32)
-// is the reference's wrapping sum bit for bit (integer arithmetic, any order).  K1's scalar-pipe version
+// is the reference's wrapping sum bit for bit (integer arithmetic, any order).  The scalar-pipe version
 // (keyswitch.cu) spends 24.6 M thread instructions per ciphertext on a decode -> compare -> branch chain
 // (profiles/r01_ncu_k2_splits.txt); here the selection IS the matrix product.
 //
