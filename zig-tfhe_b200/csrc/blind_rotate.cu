@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
                 const uint32_t *accp = h ? acc_b : acc_a;
                 uint32_t d[16];
                 load_rot_diffs(d, accp, at, offset, hi, lo);
-#pragma unroll (LT > 0 ? LT : 1)
+#pragma unroll (LT > 0 ? LT : 1)   // (rolled, constants still compile-time: 96.5 k instead of 103.0 k bootstraps/s at six per CTA)
                 for (int l = 0; l < L; l++) {
                     cplx v[8];
                     digits_to_cplx(v, d, 32 - (l + 1) * bgbit, mask, half_bg);
