@@ -58,6 +58,11 @@ int main(int argc, char **argv) {
         tfhe_b200::saveCloudKey(key_path, p, tfhe_b200::CloudKey{0x82080000u, bsk.data(), ksk.data()});
         tfhe_b200::GpuBootstrap from_file(p, key_path);
         if (from_file.bootstrap(in[0].first) != boot) return 6;
+        // two functions from one blind rotation (tfhe_b200_lut_bootstrap_many_batch) and the documented bootstrapLut, through the C++ mirror
+        const std::vector<uint32_t> ident = {0x00000000u, 0x20000000u, 0x40000000u, 0x60000000u}, shifted = {0x20000000u, 0x40000000u, 0x60000000u, 0x00000000u};
+        auto many = bs.bootstrapLutMany(in[0].first, {ident, shifted});
+        if (many.size() != 2 || many[0].size() != w || many[1].size() != w || many[0] == many[1]) return 7;
+        if (bs.bootstrapLut(in[0].first, ident).size() != w) return 8;
         std::printf("ok strategy=%s count=%zu\n", gates.bootstrapStrategy(), count);
     } catch (const tfhe_b200::Error &e) {
         std::printf("error %d: %s\n", e.code, e.what());
