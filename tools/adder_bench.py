@@ -17,6 +17,9 @@ params = tfhe_b200.PARAM_SETS["128"]
 sk, ck = HK.gen_cloud_key(params, seed=1)
 ctx = tfhe_b200.Context(params, devices=[0])
 ctx.load_cloud_key(ck)
+for kv in sys.argv[2:]:          # extra tuning keys, e.g. twt=-1 (round-1 kernels: four ciphertexts per CTA in the lanes)
+    k, v = kv.split("=")
+    ctx.set_tuning(k, int(v))
 rng = np.random.default_rng(7)
 x = rng.integers(0, 2**16, B); y = rng.integers(0, 2**16, B)
 x[0], y[0] = 402, 304
