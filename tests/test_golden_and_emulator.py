@@ -85,7 +85,7 @@ def test_exact_tables_are_conjugate_and_exact_forward_matches_oracle(emu):
         assert (out * 2.0 == O.ifft1024(poly.view(np.uint32))).all()
 
 
-@pytest.mark.parametrize("name,modulus", [("uint4", 16), ("uint1", 2), ("uint2", 4), ("128", 4)])
+@pytest.mark.parametrize("name,modulus", [("uint4", 16), ("uint1", 2), ("uint2", 4), ("128", 4), ("uint3", 8), ("uint6", 64), ("uint8", 256)])
 def test_emulated_exact_blind_rotation_is_bit_exact(emu, name, modulus):
     """exact-mode arithmetic (same __host__ __device__ code as blind_rotate_exact_rb_kernel) == oracle on every coefficient
     of every iteration, on the large-digit sets where the fast transform rounds differently"""

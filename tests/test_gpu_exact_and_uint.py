@@ -83,6 +83,37 @@ def test_fast_mode_uint_sets_decode(name, modulus):
         c.close()
 
 
+@pytest.mark.parametrize("name,modulus", [("uint3", 8), ("uint5", 32), ("uint6", 64), ("uint7", 128), ("uint8", 256)])
+def test_exact_mode_remaining_uint_sets_blind_rotation_bit_exact(name, modulus):
+    """the UINT sets BASELINE config 4 does not quote (params.zig:180-375): n up to 1160, BGBIT 23 (UINT3, generic instantiation) and
+    22; real bootstrapping keys (their key-switching keys run to 1.8 GB and are covered by the structural test below), every CTA
+    width of the exact kernel across a wave boundary, bit for bit against the oracle, where the reference's saturating
+    float -> integer casts decide the result"""
+    import tfhe_b200
+    orc = O.Oracle(name); k = keys_for(name, with_ksk=False)
+    c = tfhe_b200.Context(name, devices=[0])
+    try:
+        c.load_key(k.bsk, None, k.offset)
+        c.set_mode(tfhe_b200.MODE_EXACT)
+        B = 148 + 7
+        rng = np.random.default_rng(12)
+        msgs = rng.integers(0, modulus, B).astype(np.uint32)
+        ct = orc.encrypt_lwe_messages(msgs, modulus, k, seed=9)
+        tv = orc.lut_generate(np.array([(5 * x + 3) % modulus for x in range(modulus)], np.uint32), modulus)
+        got = c.blind_rotate_batch(ct, tv)
+        sel = np.array([0, 1, 5, 6, 147, 148, B - 1])
+        ref = orc.blind_rotate_batch(ct[sel], k, tv)
+        assert (got[sel] == ref).all(), f"{(got[sel] != ref).sum()} coefficients differ"
+        for kct in (1, 4, 6):
+            c.set_tuning("exact_kct", kct)
+            assert (c.blind_rotate_batch(ct[:13], tv) == got[:13]).all(), kct
+        c.set_tuning("exact_kct", 0)
+        c.set_mode(tfhe_b200.MODE_FAST)      # fast mode: same sizes through the production kernel (not the parity mode on these sets)
+        assert c.blind_rotate_batch(ct[:13], tv).shape == (13, 2, 1024)
+    finally:
+        c.close()
+
+
 def test_keyswitch_generic_base_bit_exact():
     import tfhe_b200
     c, orc, k = _ctx("uint4", tfhe_b200.MODE_FAST)

@@ -521,7 +521,9 @@ cudaError_t launch_blind_rotate_exact(const BrArgs &a, const ExactArgs &x, bool 
         if (kct < 1 || kct > 6 || kct == 5) {
             // six ciphertexts per CTA (tensor-memory twiddles, profiles/r02_k1x_dense.log) from one full wave of them up, unless
             // margin tracking is on; else the fewest waves of up to four, and below one wave the narrowest CTA that covers the batch
-            if (a.B >= sms * 6 && !track_margin && a.n <= 1024) kct = 6;
+            // (n = 1160, UINT7/8, still fits the 227 KiB of shared memory with 80 bytes to spare; the largest supported n = 1279 does not)
+            const bool fits6 = ex_fixed_bytes() + 6 * (size_t)ex_group_bytes(a.n, true) <= 232448;
+            if (a.B >= sms * 6 && !track_margin && fits6) kct = 6;
             else {
                 kct = 4;
                 for (int k = 1; k <= 4; k++)
