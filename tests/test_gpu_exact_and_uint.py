@@ -85,7 +85,7 @@ def test_fast_mode_uint_sets_decode(name, modulus):
 
 @pytest.mark.parametrize("name,modulus", [("uint3", 8), ("uint5", 32), ("uint6", 64), ("uint7", 128), ("uint8", 256)])
 def test_exact_mode_remaining_uint_sets_blind_rotation_bit_exact(name, modulus):
-    """the UINT sets BASELINE config 4 does not quote (params.zig:180-375): n up to 1160, BGBIT 23 (UINT3, generic instantiation) and
+    """the UINT sets BASELINE config 4 does not quote (params.zig:180-375): n up to 1160, BGBIT 23 (UINT3) and
     22; real bootstrapping keys (their key-switching keys run to 1.8 GB and are covered by the structural test below), every CTA
     width of the exact kernel across a wave boundary, bit for bit against the oracle, where the reference's saturating
     float -> integer casts decide the result"""
@@ -182,17 +182,21 @@ def test_exact_register_blocked_equals_legacy_and_oracle(name, modulus):
         c.close()
 
 
-def test_fast_mode_uint4_instantiations_agree():
-    """fast mode at UINT4 is not the parity mode, but its kernels must agree with each other: the L = 1 /
-    BGBIT = 22 instantiation of the six-per-CTA kernel (full waves) against the generic four-per-CTA kernel, word for word"""
+@pytest.mark.parametrize("name,modulus", [("uint1", 2), ("uint2", 4), ("uint3", 8), ("uint4", 16), ("uint8", 256)])
+def test_fast_mode_uint_instantiations_agree(name, modulus):
+    """fast mode on the UINT sets is not the parity mode, but its kernels must agree with each other: the
+    gadget-shape instantiations of the six-per-CTA kernel (L = 2 / BGBIT = 10, L = 1 / BGBIT = 18, 23, 22; full waves) against the
+    generic four-per-CTA kernel and the round-1 kernels, word for word"""
     import tfhe_b200
-    c, orc, k = _ctx("uint4", tfhe_b200.MODE_FAST)
+    orc = O.Oracle(name); k = keys_for(name, with_ksk=False)
+    c = tfhe_b200.Context(name, devices=[0])
     try:
+        c.load_key(k.bsk, None, k.offset)
         B = 148 * 6 + 40
         rng = np.random.default_rng(12)
-        ct = orc.encrypt_lwe_messages(rng.integers(0, 16, B).astype(np.uint32), 16, k, seed=3)
-        tv = orc.lut_generate(np.arange(16, dtype=np.uint32), 16)
-        a = c.blind_rotate_batch(ct, tv)                 # 888 on the L = 1 instantiation + a 40-ciphertext tail
+        ct = orc.encrypt_lwe_messages(rng.integers(0, modulus, B).astype(np.uint32), modulus, k, seed=3)
+        tv = orc.lut_generate(np.arange(modulus, dtype=np.uint32), modulus)
+        a = c.blind_rotate_batch(ct, tv)                 # 888 on the instantiation + a 40-ciphertext tail
         c.set_tuning("kct", 4)
         b = c.blind_rotate_batch(ct, tv)
         c.set_tuning("kct", 0); c.set_tuning("twt", -1)

@@ -24,7 +24,10 @@ ctx.set_mode(tfhe_b200.MODE_EXACT)
 ctx.set_tuning("timing", 1)
 for kv in sys.argv[3:]:
     k, v = kv.split("=")
-    ctx.set_tuning(k, int(v))
+    if k == "mode":          # mode=fast: the production kernel on the same inputs
+        ctx.set_mode(tfhe_b200.MODE_FAST if v == "fast" else tfhe_b200.MODE_EXACT)
+    else:
+        ctx.set_tuning(k, int(v))
 for _ in range(2):
     out = ctx.bootstrap_batch(ct, tv) if name == "uint4" else ctx.blind_rotate_batch(ct, tv)
     print("K1x ms", ctx.last_kernel_ms(0, 0), "K2 ms", ctx.last_kernel_ms(0, 1), "->", B / ctx.last_kernel_ms(0, 0) * 1e3, "bootstraps/s")

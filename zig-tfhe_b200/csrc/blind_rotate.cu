@@ -256,8 +256,17 @@ struct Layout {
     }
 };
 
-template <int KCT, bool USE_TMA, bool MARGIN, int TEAM = 1, int LT = 0, int TWT = 0>
+// genDecompositionOffset (src/key.zig:121-131) of a gadget shape
+__host__ __device__ constexpr uint32_t gadget_offset(int L, int bgbit) {
+    uint32_t o = 0u;
+    for (int i = 0; i < L; i++) o += (1u << (bgbit - 1)) << (32 - (i + 1) * bgbit);
+    return o;
+}
+static_assert(gadget_offset(3, 6) == 0x82080000u && gadget_offset(1, 22) == 0x80000000u && gadget_offset(2, 10) == 0x80200000u, "key.zig:121-131");
+
+template <int KCT, bool USE_TMA, bool MARGIN, int TEAM = 1, int LT = 0, int TWT = 0, int BGT = (LT == 3 ? 6 : LT == 1 ? 22 : 0)>
 __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(const BrArgs P) {
+    static_assert((LT == 0) == (BGT == 0), "gadget length and digit width are compile-time constants together");
     using Lay = Layout<KCT, TEAM, (TWT != 0 && KCT > 4)>;
     static_assert(TWT == 0 || TEAM == 1 || KCT > 4, "teams of two with tensor-memory twiddles: six ciphertexts per CTA only");
     constexpr bool XA = Lay::kX1Alias;
@@ -277,8 +286,9 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(ptr + 64);
     uint32_t *ring_cnt = reinterpret_cast<uint32_t *>(ptr + 80);   // [kMaxStages] releases per stage, monotone
     ptr += 96;
-    // LT = 3: the L = 3 / BGBIT = 6 sets (80/110/128-bit).  LT = 1: L = 1 / BGBIT = 22 (UINT4 ... UINT8; offset 2^31, wide rounding)
-    const int n = P.n, L = LT > 0 ? LT : P.L, bgbit = LT == 3 ? 6 : LT == 1 ? 22 : P.bgbit;
+    // LT / BGT > 0: gadget shape as compile-time constants.  3 / 6: the 80/110/128-bit sets; 1 / 22: UINT4 ... UINT8; 1 / 23: UINT3;
+    // 1 / 18: UINT2; 2 / 10: UINT1 (all but the first with the wide rounding; the launcher checks offset and rounding mode)
+    const int n = P.n, L = LT > 0 ? LT : P.L, bgbit = LT > 0 ? BGT : P.bgbit;
     static_assert(TEAM == 1 || (TEAM == 2 && KCT % 2 == 0), "a team never straddles CTAs");
     constexpr int kTeamThreads = TEAM * kGroupThreads;
     const int group_bytes = Lay::group_bytes(n);
@@ -411,8 +421,9 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
     bar_sync(barid, kTeamThreads);
 
     const uint32_t mask = (1u << bgbit) - 1u, half_bg = 1u << (bgbit - 1);
-    const uint32_t offset = LT == 3 ? 0x82080000u : LT == 1 ? 0x80000000u : P.offset;   // genDecompositionOffset for L = 3 / BGBIT = 6 (src/key.zig:121-131); the launcher checks it
-    const int wide = LT == 3 ? 0 : LT == 1 ? 1 : P.wide_round;   // BGBIT = 6: magic-add rounding (coefficients < 2^45)
+    constexpr uint32_t kOffset = gadget_offset(LT > 0 ? LT : 1, BGT > 0 ? BGT : 1);
+    const uint32_t offset = LT > 0 ? kOffset : P.offset;   // the launcher checks it
+    const int wide = LT == 3 ? 0 : LT > 0 ? 1 : P.wide_round;   // BGBIT = 6: magic-add rounding (coefficients < 2^45)
     int stage = 0;
     uint32_t phase = 0;
     double margin = 0.0;
@@ -945,8 +956,13 @@ cudaError_t launch_twt(const BrArgs &a, cudaStream_t s) {
     const size_t smem = Lay::kStages * kBskChunkBytes + 96 + (size_t)KCT * Lay::group_bytes(a.n);
     auto kern = blind_rotate_kernel<KCT, true, false, TEAM, 0, 1>;
     if (a.L == 3 && a.bgbit == 6 && a.offset == 0x82080000u && !a.wide_round && kUnrollL3) kern = blind_rotate_kernel<KCT, true, false, TEAM, 3, 1>;
-    if (KCT == 6 && a.L == 1 && a.bgbit == 22 && a.offset == 0x80000000u && a.wide_round && kUnrollL3)
-        kern = blind_rotate_kernel<KCT, true, false, TEAM, (KCT == 6 ? 1 : 0), 1>;
+    constexpr bool kInst = KCT == 6;   // the UINT gadget shapes: at the full-wave width only
+    if (kInst && a.wide_round && kUnrollL3 && a.L >= 1 && a.L <= 2 && a.bgbit >= 1 && a.L * a.bgbit <= 32 && a.offset == gadget_offset(a.L, a.bgbit)) {
+        if (a.L == 1 && a.bgbit == 22) kern = blind_rotate_kernel<KCT, true, false, TEAM, (kInst ? 1 : 0), 1, (kInst ? 22 : 0)>;        // UINT4 ... UINT8
+        else if (a.L == 1 && a.bgbit == 23) kern = blind_rotate_kernel<KCT, true, false, TEAM, (kInst ? 1 : 0), 1, (kInst ? 23 : 0)>;   // UINT3
+        else if (a.L == 1 && a.bgbit == 18) kern = blind_rotate_kernel<KCT, true, false, TEAM, (kInst ? 1 : 0), 1, (kInst ? 18 : 0)>;   // UINT2
+        else if (a.L == 2 && a.bgbit == 10) kern = blind_rotate_kernel<KCT, true, false, TEAM, (kInst ? 2 : 0), 1, (kInst ? 10 : 0)>;   // UINT1
+    }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<(a.B + KCT - 1) / KCT, KCT * kGroupThreads, smem, s>>>(a);

@@ -493,7 +493,12 @@ cudaError_t launch_rb(const BrArgs &a, const ExactArgs &x, const ExactConsts &kc
     const size_t smem = ex_fixed_bytes() + (size_t)KCT * ex_group_bytes(a.n, KCT > 4);
     auto k0 = blind_rotate_exact_rb_kernel<KCT, false>;
     auto k1 = blind_rotate_exact_rb_kernel<KCT, true>;
-    if (KCT >= 4 && a.L == 1 && a.bgbit == 22) k0 = blind_rotate_exact_rb_kernel<KCT, false, (KCT >= 4 ? 1 : 0), (KCT >= 4 ? 22 : 0)>;   // UINT4 (and UINT5-8)
+    // gadget shape as compile-time constants at the two widths full waves run at (KCT < 4: generic kernel only)
+    constexpr bool kInst = KCT >= 4;
+    if (kInst && a.L == 1 && a.bgbit == 22) k0 = blind_rotate_exact_rb_kernel<KCT, false, (kInst ? 1 : 0), (kInst ? 22 : 0)>;        // UINT4 ... UINT8
+    else if (kInst && a.L == 1 && a.bgbit == 23) k0 = blind_rotate_exact_rb_kernel<KCT, false, (kInst ? 1 : 0), (kInst ? 23 : 0)>;   // UINT3
+    else if (kInst && a.L == 1 && a.bgbit == 18) k0 = blind_rotate_exact_rb_kernel<KCT, false, (kInst ? 1 : 0), (kInst ? 18 : 0)>;   // UINT2
+    else if (kInst && a.L == 2 && a.bgbit == 10) k0 = blind_rotate_exact_rb_kernel<KCT, false, (kInst ? 2 : 0), (kInst ? 10 : 0)>;   // UINT1
     // (L = 3 / BGBIT = 6 the same way: 76.1 k against 77.0 k bootstraps/s at the 128-bit set in exact mode -- the unrolled digit loop spills; not instantiated)
     cudaError_t e = cudaFuncSetAttribute(margin ? k1 : k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
