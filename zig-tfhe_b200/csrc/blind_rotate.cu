@@ -67,6 +67,11 @@ constexpr bool kUnrollL3 = false;
 #else
 constexpr bool kUnrollL3 = true;
 #endif   // L = 3 / BGBIT = 6 instantiation of the throughput kernel (false: generic kernel only, for A/B runs)
+#ifdef TFHE_B200_SEQ_INVERSE
+constexpr bool kPairInverse = false;
+#else
+constexpr bool kPairInverse = true;
+#endif   // the two inverse transforms of a step pipelined against each other (inv_transform_pair); false: one after the other
 
 // Twiddles r^1..r^7 of one thread for one pass.  MODE 0: all seven resident (28 registers, KCT <= 4);
 // MODE 1: r, r^2, r^4 resident and the rest expanded per pass (12 registers); MODE 2: read from a shared-memory
@@ -181,6 +186,57 @@ __device__ __forceinline__ void inv_transform(cplx (&v)[8], Xbuf &xb, const Tw2<
     for (int q = 0; q < 8; q++) v[q] = x1[ALIAS ? x1a_slot(hi, q, lo) : x1_slot(hi, q, lo)];
     }
     inv_pass1(v);
+}
+
+// Both inverse transforms of a CMUX step (the a and b halves of the external product) software-pipelined against each other, for the
+// layout with X1 laid over the X2 buffers (Layout::kX1Alias, double-buffered X2).  Same arithmetic per polynomial as inv_transform;
+// a goes through the X2 buffer `flip`, b through the other one, and each group barrier of one polynomial is covered by a pass of the
+// other: three group barriers instead of four, and the shared-memory round trips of one overlap the butterflies of the other.
+//   buffer F = flip: free on entry (DBX2 argument of inv_transform).  Buffer G = the last forward transform's X2: its forward reads
+//   are finished by everybody once bar 1 is passed.  X1 of a reuses F after bar 2 (all X2 reads of F precede it), X1 of b reuses G
+//   after bar 3.  `flip` is unchanged on exit, as after two sequential transforms.
+// FIN(v, which) consumes a finished polynomial (rounding + accumulation), a's before b's last pass to free its registers.
+template <int POW, int POW3, class Fin>
+__device__ __forceinline__ void inv_transform_pair(cplx (&a)[8], cplx (&b)[8], Xbuf &xb, const Tw2<POW> &tw2, const Tw2<POW3> &tw3, int hi, int lo,
+                                                   int barid, int nthr, Fin fin) {
+    cplx *bf = xb.x2 + xb.flip, *bg = xb.x2 + (xb.flip ^ kX2Slots);
+    {
+        cplx w[7];
+        tw3.get(w);
+        inv_pass(a, w, 1);
+#pragma unroll
+        for (int q = 0; q < 8; q++) bf[x2_slot(hi, lo, q)] = a[q];
+        inv_pass(b, w, 1);
+    }
+    bar_sync(barid, nthr);   // 1: a's X2 writes are visible; nobody still reads G (forward X2 of the step's last digit transform)
+#pragma unroll
+    for (int q = 0; q < 8; q++) a[q] = bf[x2_slot(lo, q, hi)];
+#pragma unroll
+    for (int q = 0; q < 8; q++) bg[x2_slot(hi, lo, q)] = b[q];
+    {
+        cplx w[7];
+        tw2.get(w);
+        inv_pass(a, w, 1);
+        bar_sync(barid, nthr);   // 2: b's X2 writes are visible; everybody has finished its X2 reads of F
+#pragma unroll
+        for (int q = 0; q < 8; q++) b[q] = bg[x2_slot(lo, q, hi)];
+#pragma unroll
+        for (int q = 0; q < 8; q++) bf[x1a_slot(hi, lo, q)] = a[q];   // X1 of a in this warp's rows of F
+        inv_pass(b, w, 1);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; q++) a[q] = bf[x1a_slot(hi, q, lo)];
+    inv_pass1(a);
+    fin(a, 0);
+    bar_sync(barid, nthr);   // 3: everybody has finished its X2 reads of G
+#pragma unroll
+    for (int q = 0; q < 8; q++) bg[x1a_slot(hi, lo, q)] = b[q];
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; q++) b[q] = bg[x1a_slot(hi, q, lo)];
+    inv_pass1(b);
+    fin(b, 1);
 }
 
 // 8 complex accumulators <-> 32 TMEM columns of this thread's lane
@@ -511,10 +567,16 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
                     }
                 }
             }
-            inv_transform<USE_TMA, DBX2, POW, POW3, XA>(oa, xb, tw2, tw3, hi, lo, barid, pr, kTeamThreads, diag);
-            round_accumulate<MARGIN>(oa, acc_a, t, wide, margin);
-            inv_transform<USE_TMA, DBX2, POW, POW3, XA>(ob, xb, tw2, tw3, hi, lo, barid, pr, kTeamThreads, diag);
-            round_accumulate<MARGIN>(ob, acc_b, t, wide, margin);
+            if constexpr (XA && DBX2 && kPairInverse) {
+                inv_transform_pair<POW, POW3>(oa, ob, xb, tw2, tw3, hi, lo, barid, kTeamThreads, [&](const cplx (&v)[8], int which) {
+                    round_accumulate<MARGIN>(v, which ? acc_b : acc_a, t, wide, margin);
+                });
+            } else {
+                inv_transform<USE_TMA, DBX2, POW, POW3, XA>(oa, xb, tw2, tw3, hi, lo, barid, pr, kTeamThreads, diag);
+                round_accumulate<MARGIN>(oa, acc_a, t, wide, margin);
+                inv_transform<USE_TMA, DBX2, POW, POW3, XA>(ob, xb, tw2, tw3, hi, lo, barid, pr, kTeamThreads, diag);
+                round_accumulate<MARGIN>(ob, acc_b, t, wide, margin);
+            }
         } else {
             // ---- accumulators in TMEM (168-register budget): each half is loaded, updated and stored back
 #pragma unroll 1
@@ -568,8 +630,12 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
                 round_accumulate<MARGIN>(o, ab ? acc_b : acc_a, t, wide, margin);
             }
         }
-        bar_sync(barid, kTeamThreads);   // accumulator complete before the next rotated reads
+        // accumulator complete before the next rotated reads.  With the paired inverse the a half is complete at its third barrier
+        // (fin(a) precedes it) and the b half is not read before at least one more group barrier, of the next step's first digit transform;
+        // the buffers the next step touches first (X1 in this warp's rows of G, X2 in F) are free by then as well.
+        if constexpr (!(XA && DBX2 && kPairInverse)) bar_sync(barid, kTeamThreads);
     }
+    if constexpr (XA && DBX2 && kPairInverse) bar_sync(barid, kTeamThreads);
 
     // ---- epilogue
     if (live && P.out_trlwe) {
