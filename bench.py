@@ -256,6 +256,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pageable", action="store_true", help="e2e leg from pageable host memory (what a Zig caller's page_allocator gives)")
     ap.add_argument("--host-copy-threads", type=int, default=-1, help="tuning key host_copy_threads for the e2e leg (-1: library default)")
+    ap.add_argument("--host-pipeline", type=int, default=-1, help="tuning key host_pipeline for the e2e leg (-1: library default)")
     args = ap.parse_args()
     if args.mode is None:
         args.mode = "exact" if args.params.startswith("uint") else "fast"
@@ -379,6 +380,8 @@ def main():
     ctx.set_tuning("timing", 0)
     if args.host_copy_threads >= 0:
         ctx.set_tuning("host_copy_threads", args.host_copy_threads)
+    if args.host_pipeline >= 0:
+        ctx.set_tuning("host_pipeline", args.host_pipeline)
     out_np = h_out.numpy().view(np.uint32)
     if is_lut:
         a_np, tv_np = h_a.numpy().view(np.uint32), h_tv.numpy().view(np.uint32)

@@ -257,7 +257,7 @@ uint64_t tfhe_b200_launch_count(const tfhe_b200_ctx *ctx);
  * up on the BASEBIT = 2 sets, 1 = always there, -1 = never), "exact_kct" ciphertexts per CTA of the exact kernel (0 = automatic,
  * 1..4, 6), "exact_legacy" 1 = round-1 exact kernel, "host_copy_threads" memcpy threads that stage large PAGEABLE host buffers
  * through pinned memory (default 8, 0 = plain cudaMemcpyAsync), "host_pipeline" 1 = gate / bootstrap batches of >= 32,768 ciphertexts per
- * device from pageable memory run as four chunks whose staging overlaps the kernels (default), "inject_fault" test hook: device value - 1 fails its next
+ * device run as four chunks whose copies (staging, from pageable memory) overlap the kernels (default; 2 = pageable callers only, 0 = never), "inject_fault" test hook: device value - 1 fails its next
  * host-batch shard, "use_tma" 0/1, "latency_mode" (1 = automatic: batches <= SMs/2 on two-CTA clusters, <= SMs
  * on one CTA per ciphertext; 2 = never the cluster kernel; 0 = throughput kernel only), "team" (2: two ciphertexts per
  * warp, a measured K1 variant kept for A/B runs), "max_chunk" ciphertexts per launch, "timing" 0/1 (record CUDA events

