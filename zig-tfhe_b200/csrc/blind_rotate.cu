@@ -272,8 +272,15 @@ __device__ __forceinline__ void round_accumulate(const cplx (&v)[8], uint32_t *a
         }
         const uint32_t r0 = wide ? round_torus_wide(v[p].re) : round_torus_magic(v[p].re);
         const uint32_t r1 = wide ? round_torus_wide(v[p].im) : round_torus_magic(v[p].im);
+        // one shared-memory reduction per word instead of a load, an add and a store: half the accumulator wavefronts and no
+        // load-to-store dependency (105.8 k against 104.8 k bootstraps/s at six per CTA; -DTFHE_B200_RMW_ACC builds the old form)
+#ifdef TFHE_B200_RMW_ACC
         accp[e] += r0;
         accp[e + kHalfN] += r1;
+#else
+        atomicAdd(&accp[e], r0);
+        atomicAdd(&accp[e + kHalfN], r1);
+#endif
     }
 }
 

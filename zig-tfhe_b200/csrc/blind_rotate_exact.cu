@@ -457,8 +457,8 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1)
                 double r_re, r_im;
                 const uint32_t u_re = ex_round_torus(r.re, &r_re), u_im = ex_round_torus(r.im, &r_im);
                 if (MARGIN) margin = fmax(margin, fmax(fabs(r.re - r_re), fabs(r.im - r_im)));
-                accp[64 * p + t] += u_re;
-                accp[64 * p + t + kHalfN] += u_im;
+                atomicAdd(&accp[64 * p + t], u_re);          // shared-memory reduction: no load-to-store dependency (see round_accumulate)
+                atomicAdd(&accp[64 * p + t + kHalfN], u_im);
             }
         }
         bar_sync(barid, kGroupThreads);   // accumulator complete before the next rotated reads
