@@ -530,7 +530,9 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
             cplx oa[8], ob[8];
 #pragma unroll
             for (int q = 0; q < 8; q++) { oa[q] = cplx{0.0, 0.0}; ob[q] = cplx{0.0, 0.0}; }
-#pragma unroll 1   // (unrolled: 97.2 k instead of 103.0 k bootstraps/s at six per CTA, instruction footprint)
+// (unrolled at L = 3: 97.2 k instead of 103.0 k bootstraps/s at six per CTA; at L = 1, one digit transform per polynomial, it pays: UINT4
+// fast mode 187.6 k -> 191.9 k, UINT2 223.4 k -> 228.6 k blind rotations/s, as in the exact kernel)
+#pragma unroll (LT == 1 ? 2 : 1)
             for (int h = 0; h < 2; h++) {          // h = 0: digits of the a polynomial, 1: of b (trgsw.zig:211-217)
                 const uint32_t *accp = h ? acc_b : acc_a;
                 uint32_t d[16];
