@@ -639,12 +639,13 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1) blind_rotate_kernel(co
                 round_accumulate<MARGIN>(o, ab ? acc_b : acc_a, t, wide, margin);
             }
         }
-        // accumulator complete before the next rotated reads.  With the paired inverse the a half is complete at its third barrier
-        // (fin(a) precedes it) and the b half is not read before at least one more group barrier, of the next step's first digit transform;
-        // the buffers the next step touches first (X1 in this warp's rows of G, X2 in F) are free by then as well.
-        if constexpr (!(XA && DBX2 && kPairInverse)) bar_sync(barid, kTeamThreads);
+        // accumulator complete before the next rotated reads.  With a double-buffered X2 no barrier is needed here: the a half's
+        // add-back is followed by a group barrier of the b half's inverse transform (the pair's third barrier), the b half is not read
+        // before at least one more group barrier, of the next step's first digit transform, and the buffers the next step touches
+        // first are free by then (tests/test_exchange_protocol.py checks this protocol as a model, for every kernel layout).
+        if constexpr (!DBX2 || ACCT) bar_sync(barid, kTeamThreads);
     }
-    if constexpr (XA && DBX2 && kPairInverse) bar_sync(barid, kTeamThreads);
+    if constexpr (DBX2 && !ACCT) bar_sync(barid, kTeamThreads);   // the epilogue reads other threads' coefficients
 
     // ---- epilogue
     if (live && P.out_trlwe) {

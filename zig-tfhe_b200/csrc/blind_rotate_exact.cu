@@ -461,8 +461,10 @@ __global__ void __launch_bounds__(KCT * kGroupThreads, 1)
                 atomicAdd(&accp[64 * p + t + kHalfN], u_im);
             }
         }
-        bar_sync(barid, kGroupThreads);   // accumulator complete before the next rotated reads
+        // (no barrier at the end of a step: each half's add-back is followed by a group barrier -- the other half's transform, or the
+        // next step's first digit transform -- before the rotated reads that depend on it; tests/test_exchange_protocol.py)
     }
+    bar_sync(barid, kGroupThreads);   // the epilogue reads other threads' coefficients
 
     if (P.out_trlwe) {
         uint32_t *o = P.out_trlwe + ct * (size_t)(2 * kN);
