@@ -180,6 +180,25 @@ def test_other_kernels_need_no_end_of_step_barrier(stepfn, L):
         assert races(prog) == []
 
 
+@pytest.mark.parametrize("L", [1, 3])
+def test_every_remaining_barrier_is_needed(L):
+    """minimality: dropping any one of the 2 L + 3 group barriers of a step (in every step) produces a conflict"""
+    for k in range(2 * L + 3):
+        prog, flip = [BAR], 0
+        for _ in range(4):
+            s, flip = step(flip, L)
+            seen, kept = 0, []
+            for ev in s:
+                if ev == BAR:
+                    if seen != k:
+                        kept.append(ev)
+                    seen += 1
+                else:
+                    kept.append(ev)
+            prog += kept
+        assert races(prog), f"barrier {k} of a step would be redundant"
+
+
 def test_third_barrier_of_the_pair_is_needed():
     """bar 3 orders everybody's X2 reads of G before b's X1 reuses G -- and a's add-back before the next step's rotated reads"""
     bad = run(3, bar3=False)
